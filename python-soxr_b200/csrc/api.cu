@@ -1,0 +1,544 @@
+// api.cu -- the C ABI of libb200soxr.so (include/b200soxr.h).
+//
+// Host-side mirror of libsoxr's public API for the constant-rate path
+// (libsoxr/src/soxr.c) plus the batch entry point that replaces the per-clip
+// driver loops of python-soxr's nanobind binding (src/soxr_ext.cpp:210-402).
+// There is NO CPU fallback: without a usable CUDA device every compute entry
+// point returns an error string.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <vector>
+
+#include "../../include/b200soxr.h"
+#include "plan.h"
+#include "runtime.h"
+
+using namespace b2;
+
+namespace {
+
+const char *kNoDevice = "b200soxr: no usable CUDA device (this library has no CPU fallback)";
+
+bool device_ok() {
+  static int state = -1;
+  if (state < 0) {
+    int n = 0;
+    state = (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) ? 1 : 0;
+    if (!state) cudaGetLastError();
+  }
+  return state == 1;
+}
+
+QSpec to_qspec(const b200soxr_quality_spec_t &q) {
+  QSpec s;
+  s.precision = q.precision;
+  s.phase_response = q.phase_response;
+  s.passband_end = q.passband_end;
+  s.stopband_begin = q.stopband_begin;
+  s.flags = q.flags;
+  s.error = static_cast<const char *>(q.e);
+  // backwards compatibility with the original API (soxr.c:408-413)
+  if (s.passband_end > 2) s.passband_end /= 100;
+  if (s.stopband_begin > 2) s.stopband_begin = 2 - s.stopband_begin / 100;
+  return s;
+}
+RSpec to_rspec(const b200soxr_runtime_spec_t *r) {
+  RSpec s;
+  if (r) {
+    s.log2_min_dft_size = r->log2_min_dft_size;
+    s.log2_large_dft_size = r->log2_large_dft_size;
+    s.coef_size_kbytes = r->coef_size_kbytes;
+    s.flags = r->flags;
+  }
+  return s;
+}
+const double kFullScale[] = {1, 1, 65536. * 32768, 32768};   // soxr.c:377
+
+size_t div_len_of(double in_rate, double out_rate) {          // soxr_ext.cpp:71,239
+  return size_t(std::max(1000., 48000 * in_rate / out_rate));
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// stream handle
+// ---------------------------------------------------------------------------
+struct b200soxr {
+  unsigned channels = 0;
+  double io_ratio = 0;
+  b200soxr_io_spec_t io{};
+  QSpec q;
+  RSpec r;
+  bool device_io = false;
+  std::shared_ptr<DevicePlan> dp;
+  std::unique_ptr<CallEmu> emu;
+  Workspace *ws = nullptr;
+  cudaStream_t stream = nullptr;
+  DevBuf xbuf, clips_dev, seed_dev;
+  size_t x_cap = 0;       // elements per signal in xbuf
+  long x_base = 0, x_hi = 0, n_in_total = -1, out_done = 0;
+  size_t clips = 0;
+  unsigned long long seed = 0;
+  bool flushing = false;
+  const char *error = nullptr;
+  std::vector<const void *> in_ptrs;
+  std::vector<void *> out_ptrs;
+
+  ~b200soxr() {
+    xbuf.release();
+    clips_dev.release();
+    seed_dev.release();
+    if (ws) release_workspace(ws);
+  }
+  size_t esz() const { return dp->is_double ? 8 : 4; }
+  const char *init_state() {
+    emu.reset(new CallEmu(dp->plan));
+    x_base = x_hi = out_done = 0;
+    n_in_total = -1;
+    flushing = false;
+    return nullptr;
+  }
+  // make room for `extra` more samples per signal, dropping history no output can need
+  const char *grow_history(size_t extra) {
+    const long keep_from = std::max(x_base, std::min(x_hi, history_needed_from(*dp, out_done)));
+    const size_t live = size_t(x_hi - keep_from);
+    const size_t es = esz();
+    if (live + extra <= x_cap) {
+      if (keep_from > x_base && live + extra + size_t(keep_from - x_base) > x_cap) {
+        // compact in place (per signal; ranges may overlap -> go through scratch)
+        if (const char *e = ws->misc.reserve(std::max<size_t>(1, live * channels) * es)) return e;
+        B2_CUDA(cudaMemcpy2DAsync(ws->misc.p, live * es, static_cast<char *>(xbuf.p) + size_t(keep_from - x_base) * es,
+                                  x_cap * es, live * es, channels, cudaMemcpyDeviceToDevice, stream));
+        B2_CUDA(cudaMemcpy2DAsync(xbuf.p, x_cap * es, ws->misc.p, live * es, live * es, channels,
+                                  cudaMemcpyDeviceToDevice, stream));
+        x_base = keep_from;
+      }
+      if (size_t(x_hi - x_base) + extra <= x_cap) return nullptr;
+    }
+    // reallocate
+    size_t new_cap = std::max<size_t>(4096, (live + extra) * 2);
+    new_cap = (new_cap + 63) & ~size_t(63);
+    DevBuf nb;
+    if (const char *e = nb.reserve(new_cap * channels * es)) return e;
+    if (live)
+      B2_CUDA(cudaMemcpy2DAsync(nb.p, new_cap * es, static_cast<char *>(xbuf.p) + size_t(keep_from - x_base) * es,
+                                x_cap * es, live * es, channels, cudaMemcpyDeviceToDevice, stream));
+    B2_CUDA(cudaStreamSynchronize(stream));
+    xbuf.release();
+    xbuf = nb;
+    x_cap = new_cap;
+    x_base = keep_from;
+    return nullptr;
+  }
+};
+
+extern "C" {
+
+b200soxr_quality_spec_t b200soxr_quality_spec(unsigned long recipe, unsigned long flags) {
+  b200soxr_quality_spec_t out;
+  std::memset(&out, 0, sizeof out);
+  const QSpec q = quality_spec(recipe, flags);
+  out.precision = q.precision;
+  out.phase_response = q.phase_response;
+  out.passband_end = q.passband_end;
+  out.stopband_begin = q.stopband_begin;
+  out.flags = q.flags;
+  out.e = const_cast<char *>(q.error);
+  return out;
+}
+
+b200soxr_io_spec_t b200soxr_io_spec(int itype, int otype) {
+  b200soxr_io_spec_t s;
+  std::memset(&s, 0, sizeof s);
+  if ((itype | otype) >= B200SOXR_SPLIT * 2 || itype < 0 || otype < 0)
+    s.e = const_cast<char *>("invalid io datatype(s)");
+  else {
+    s.itype = itype;
+    s.otype = otype;
+    s.scale = 1;
+  }
+  return s;
+}
+
+b200soxr_runtime_spec_t b200soxr_runtime_spec(unsigned num_threads) {
+  b200soxr_runtime_spec_t s;
+  std::memset(&s, 0, sizeof s);
+  s.log2_min_dft_size = 10;
+  s.log2_large_dft_size = 17;
+  s.coef_size_kbytes = 400;
+  s.num_threads = num_threads;
+  return s;
+}
+
+char const *b200soxr_version(void) { return "b200soxr-0.1.0 (libsoxr-0.1.3 compatible)"; }
+
+int b200soxr_device_available(void) { return device_ok() ? 1 : 0; }
+
+unsigned long long b200soxr_launch_count(void) { return g_launches.load(); }
+
+size_t b200soxr_output_frames(double in_rate, double out_rate, size_t ilen) {
+  return output_frames(in_rate / out_rate, ilen);
+}
+
+size_t b200soxr_plan_dump(double in_rate, double out_rate, unsigned long quality, unsigned long q_flags,
+                          char *buf, size_t buf_size) {
+  Plan p;
+  const QSpec q = quality_spec(quality, q_flags);
+  const char *err = make_plan(in_rate / out_rate, q, RSpec(), 1.0, &p);
+  std::string text = err ? std::string("error: ") + err + "\n" : p.trace;
+  if (buf && buf_size) {
+    const size_t n = std::min(buf_size - 1, text.size());
+    std::memcpy(buf, text.data(), n);
+    buf[n] = 0;
+  }
+  return text.size() + 1;
+}
+
+b200soxr_error_t b200soxr_emulate_calls(double in_rate, double out_rate, unsigned long quality,
+                                        unsigned long q_flags, size_t const *chunk_lens, size_t n_chunks,
+                                        size_t olen_each, size_t *odone_each, double *delay_each) {
+  Plan p;
+  const QSpec q = quality_spec(quality, q_flags);
+  if (const char *err = make_plan(in_rate / out_rate, q, RSpec(), 1.0, &p)) return err;
+  CallEmu emu(p);
+  for (size_t i = 0; i < n_chunks; ++i) {
+    const size_t od = chunk_lens[i] ? emu.process(chunk_lens[i], olen_each) : emu.flush(olen_each);
+    if (odone_each) odone_each[i] = od;
+    if (delay_each) delay_each[i] = emu.delay();
+  }
+  return nullptr;
+}
+
+b200soxr_t b200soxr_create(double input_rate, double output_rate, unsigned num_channels,
+                           b200soxr_error_t *error0, b200soxr_io_spec_t const *io_spec,
+                           b200soxr_quality_spec_t const *q_spec, b200soxr_runtime_spec_t const *rt_spec) {
+  const char *error = nullptr;
+  b200soxr *p = nullptr;
+  const double io_ratio = output_rate != 0 ? (input_rate != 0 ? input_rate / output_rate : -1)
+                                           : (input_rate != 0 ? -1 : 0);
+  if (q_spec && q_spec->e) error = static_cast<const char *>(q_spec->e);
+  else if (io_spec && (io_spec->e || (io_spec->itype | io_spec->otype) >= B200SOXR_SPLIT * 2))
+    error = "invalid io datatype(s)";
+  else if (!num_channels) error = "invalid # of channels";
+  else if (!(io_ratio > 0)) error = "I/O ratio out-of-range";
+  else if (!device_ok()) error = kNoDevice;
+  if (!error && !(p = new (std::nothrow) b200soxr())) error = "malloc failed";
+  if (p) {
+    p->channels = num_channels;
+    p->io_ratio = io_ratio;
+    if (io_spec) p->io = *io_spec;
+    else { std::memset(&p->io, 0, sizeof p->io); p->io.scale = 1; }
+    p->q = q_spec ? to_qspec(*q_spec) : quality_spec(B200SOXR_HQ, 0);
+    p->r = to_rspec(rt_spec);
+    p->device_io = rt_spec && (rt_spec->flags & B200SOXR_RT_DEVICE_IO);
+    if (((p->io.itype ^ p->io.otype) & B200SOXR_SPLIT))
+      error = "b200soxr: input and output must both be interleaved or both split";
+    const double scale = p->io.scale * kFullScale[p->io.otype & 3] / kFullScale[p->io.itype & 3];   // soxr.c:435-436
+    // deterministic dither seed, soxr.c:439
+    unsigned long long bits;
+    std::memcpy(&bits, &io_ratio, 8);
+    p->seed = num_channels ^ bits;
+    if (!error) error = get_device_plan(io_ratio, p->q, p->r, scale, &p->dp);
+    if (!error) {
+      p->ws = acquire_workspace();
+      p->stream = (rt_spec && rt_spec->e) ? static_cast<cudaStream_t>(rt_spec->e) : p->ws->stream;
+      error = p->clips_dev.reserve(8);
+      if (!error) error = p->seed_dev.reserve(8);
+      if (!error && cudaMemset(p->clips_dev.p, 0, 8) != cudaSuccess) error = "cudaMemset failed";
+      if (!error) error = p->init_state();
+    }
+    if (error) { delete p; p = nullptr; }
+  }
+  if (error0) *error0 = error;
+  return p;
+}
+
+double b200soxr_delay(b200soxr_t p) { return (p && !p->error && p->emu) ? p->emu->delay() : 0; }
+size_t *b200soxr_num_clips(b200soxr_t p) { return &p->clips; }
+char const *b200soxr_engine(b200soxr_t p) { return p->dp->plan.engine; }
+
+b200soxr_error_t b200soxr_clear(b200soxr_t p) {
+  if (!p) return "invalid soxr_t pointer";
+  // The reference rebuilds the resampler and zeroes everything else, incl. the
+  // clip counter and the dither seed (soxr.c:609-628).
+  p->clips = 0;
+  p->seed = 0;
+  p->error = nullptr;
+  return p->init_state();
+}
+
+void b200soxr_delete(b200soxr_t p) { delete p; }
+
+b200soxr_error_t b200soxr_process(b200soxr_t p, void const *in, size_t ilen0, size_t *idone0, void *out,
+                                  size_t olen, size_t *odone0) {
+  if (!p) return "null pointer";
+  if (p->error) return p->error;
+  size_t ilen;
+  bool flush_requested = false;
+  if (!in) { flush_requested = true; ilen = ilen0 = 0; }
+  else {
+    if ((ptrdiff_t)ilen0 < 0) { flush_requested = true; ilen0 = ~ilen0; }
+    ilen = idone0 ? std::min(size_t(std::ceil(double(olen) * p->io_ratio)), ilen0) : ilen0;   // soxr.c:736-747,775-780
+  }
+  p->flushing |= (ilen == ilen0 && flush_requested);
+  if (!out && olen) return p->error = "null output buffer pointer";
+
+  const unsigned ch = p->channels;
+  const bool split = (p->io.itype & B200SOXR_SPLIT) != 0;
+  const int it = p->io.itype & 3, ot = p->io.otype & 3;
+  cudaStream_t st = p->stream;
+  Workspace *ws = p->ws;
+  const char *e = nullptr;
+
+  // ---- input: H2D + deinterleave/convert into the device history (soxr.c:640-660)
+  if (ilen && !p->emu->flushing()) {
+    if ((e = p->grow_history(ilen))) return p->error = e;
+    const size_t isz = dtype_size(it);
+    const void *dev_in = in;
+    IoLayout lay;
+    lay.dtype = it;
+    lay.n_clips = 1;
+    lay.channels = ch;
+    if (p->device_io) {
+      if (split) return p->error = "b200soxr: device I/O supports interleaved layouts only";
+      lay.frame_stride = ch; lay.chan_stride = 1;
+    } else {
+      if ((e = ws->in_stage.reserve(ilen * ch * isz))) return p->error = e;
+      if (split) {
+        const void *const *ptrs = static_cast<const void *const *>(in);
+        for (unsigned c = 0; c < ch; ++c)
+          B2_CUDA(cudaMemcpyAsync(static_cast<char *>(ws->in_stage.p) + size_t(c) * ilen * isz, ptrs[c], ilen * isz,
+                                  cudaMemcpyHostToDevice, st));
+        lay.frame_stride = 1; lay.chan_stride = (long long)ilen;
+      } else {
+        B2_CUDA(cudaMemcpyAsync(ws->in_stage.p, in, ilen * ch * isz, cudaMemcpyHostToDevice, st));
+        lay.frame_stride = ch; lay.chan_stride = 1;
+      }
+      dev_in = ws->in_stage.p;
+    }
+    if ((e = convert_in(lay, dev_in, ilen, p->dp->is_double, p->xbuf.p, p->x_cap, size_t(p->x_hi - p->x_base), st)))
+      return p->error = e;
+    p->x_hi += long(ilen);
+    p->emu->add_input(ilen);
+  }
+  if (p->flushing && p->n_in_total < 0) p->n_in_total = p->x_hi;
+
+  // ---- output (soxr.c:664-733): how much the reference would return now
+  const size_t odone = p->emu->pull(olen, p->flushing);
+  if (odone || (ot == B200SOXR_INT16 && !(p->io.flags & B200SOXR_NO_DITHER))) {
+    const size_t es = p->esz(), osz = dtype_size(ot);
+    const size_t ys = (std::max<size_t>(odone, 1) + 63) & ~size_t(63);
+    if ((e = ws->y.reserve(ys * ch * es))) return p->error = e;
+    if (odone) {
+      XView xv{p->xbuf.p, p->x_cap, p->x_base, p->x_hi, p->n_in_total};
+      if ((e = run_range(*p->dp, xv, ch, p->out_done, p->out_done + long(odone), ws->y.p, ys, ws, st)))
+        return p->error = e;
+    }
+    IoLayout lay;
+    lay.dtype = ot;
+    lay.n_clips = 1;
+    lay.channels = ch;
+    void *dev_out = out;
+    if (p->device_io) { lay.frame_stride = ch; lay.chan_stride = 1; }
+    else {
+      if ((e = ws->out_stage.reserve(std::max<size_t>(1, odone * ch) * osz))) return p->error = e;
+      dev_out = ws->out_stage.p;
+      if (split) { lay.frame_stride = 1; lay.chan_stride = (long long)odone; }
+      else { lay.frame_stride = ch; lay.chan_stride = 1; }
+    }
+    DitherCfg dc;
+    dc.enabled = ot == B200SOXR_INT16 && !(p->io.flags & B200SOXR_NO_DITHER);
+    dc.split = split;
+    dc.seed0 = p->seed;
+    dc.call_lens.push_back((long long)odone);
+    dc.seed_end_dev = p->seed_dev.as<unsigned long long>();
+    if ((e = convert_out(lay, dev_out, 0, odone, p->dp->is_double, ws->y.p, ys, dc, p->clips_dev.as<unsigned long long>(),
+                         ws, st)))
+      return p->error = e;
+    if (!p->device_io && odone) {
+      if (split) {
+        void *const *ptrs = static_cast<void *const *>(out);
+        for (unsigned c = 0; c < ch; ++c)
+          B2_CUDA(cudaMemcpyAsync(ptrs[c], static_cast<char *>(dev_out) + size_t(c) * odone * osz, odone * osz,
+                                  cudaMemcpyDeviceToHost, st));
+      } else
+        B2_CUDA(cudaMemcpyAsync(out, dev_out, odone * ch * osz, cudaMemcpyDeviceToHost, st));
+    }
+    if (ot >= B200SOXR_INT32) {
+      unsigned long long host[2] = {0, 0};
+      B2_CUDA(cudaMemcpyAsync(&host[0], p->clips_dev.p, 8, cudaMemcpyDeviceToHost, st));
+      if (dc.enabled) B2_CUDA(cudaMemcpyAsync(&host[1], p->seed_dev.p, 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaStreamSynchronize(st));
+      p->clips = size_t(host[0]);
+      if (dc.enabled) p->seed = host[1];
+    }
+  }
+  if (!p->device_io) B2_CUDA(cudaStreamSynchronize(st));
+  p->out_done += long(odone);
+  if (idone0) *idone0 = ilen;
+  if (odone0) *odone0 = odone;
+  return nullptr;
+}
+
+b200soxr_error_t b200soxr_oneshot(double irate, double orate, unsigned num_channels, void const *in, size_t ilen,
+                                  size_t *idone, void *out, size_t olen, size_t *odone,
+                                  b200soxr_io_spec_t const *io_spec, b200soxr_quality_spec_t const *q_spec,
+                                  b200soxr_runtime_spec_t const *runtime_spec) {
+  b200soxr_error_t error = q_spec ? static_cast<const char *>(q_spec->e) : nullptr;
+  b200soxr_t h = nullptr;
+  if (!error) {
+    b200soxr_quality_spec_t q1;
+    if (!q_spec) { q1 = b200soxr_quality_spec(B200SOXR_LQ, 0); q_spec = &q1; }   // soxr.c:827-829
+    h = b200soxr_create(irate, orate, num_channels, &error, io_spec, q_spec, runtime_spec);
+  }
+  if (!error) {
+    error = b200soxr_process(h, in, ~ilen, idone, out, olen, odone);
+    b200soxr_delete(h);
+  }
+  return error;
+}
+
+// ---------------------------------------------------------------------------
+// batch entry point
+// ---------------------------------------------------------------------------
+b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *d, void const *in, void *out, size_t *odone,
+                                         size_t *clips, void *cuda_stream) {
+  if (!d) return "null pointer";
+  if (!(d->in_rate > 0) || !(d->out_rate > 0)) return "I/O ratio out-of-range";
+  if (d->dtype < 0 || d->dtype > 3) return "invalid io datatype(s)";
+  if (!d->channels || !d->n_clips) return "invalid # of channels";
+  if (!device_ok()) return kNoDevice;
+  const double io_ratio = d->in_rate / d->out_rate;
+  const QSpec q = quality_spec(d->quality, (d->flags & B200SOXR_BATCH_DOUBLE) ? B200SOXR_DOUBLE_PRECISION : 0);
+  std::shared_ptr<DevicePlan> dp;
+  if (const char *e = get_device_plan(io_ratio, q, RSpec(), 1.0, &dp)) return e;
+  const size_t total = output_frames(io_ratio, d->ilen);
+  if (odone) *odone = total;
+  if (clips) *clips = 0;
+  if (total > d->olen) return "b200soxr: output buffer too small";
+  const bool dev_ptrs = d->flags & B200SOXR_BATCH_DEVICE_PTRS;
+  const unsigned n_sig = d->n_clips * d->channels;
+  const size_t esz = dp->is_double ? 8 : 4, isz = dtype_size(d->dtype);
+
+  Workspace *ws = acquire_workspace();
+  struct Rel { Workspace *w; ~Rel() { release_workspace(w); } } rel{ws};
+  cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ws->stream;
+  const char *e = nullptr;
+
+  IoLayout li{d->dtype, d->n_clips, d->channels, d->in_clip_stride, d->in_frame_stride, d->in_chan_stride};
+  IoLayout lo{d->dtype, d->n_clips, d->channels, d->out_clip_stride, d->out_frame_stride, d->out_chan_stride};
+  auto span = [](const IoLayout &l, size_t frames) -> size_t {
+    if (!frames) return 0;
+    return size_t((l.n_clips - 1) * l.clip_stride + (long long)(frames - 1) * l.frame_stride +
+                  (l.channels - 1) * l.chan_stride + 1);
+  };
+  const void *dev_in = in;
+  void *dev_out = out;
+  const size_t in_span = span(li, d->ilen), out_span = span(lo, total);
+  if (!dev_ptrs) {
+    if ((e = ws->in_stage.reserve(std::max<size_t>(1, in_span) * isz))) return e;
+    if ((e = ws->out_stage.reserve(std::max<size_t>(1, out_span) * isz))) return e;
+    if (in_span) B2_CUDA(cudaMemcpyAsync(ws->in_stage.p, in, in_span * isz, cudaMemcpyHostToDevice, st));
+    if (out_span) B2_CUDA(cudaMemsetAsync(ws->out_stage.p, 0, out_span * isz, st));
+    dev_in = ws->in_stage.p;
+    dev_out = ws->out_stage.p;
+  }
+  if (total) {
+    // planar engine-precision input
+    const size_t xs = (std::max<size_t>(d->ilen, 1) + 63) & ~size_t(63);
+    if ((e = ws->x.reserve(xs * n_sig * esz))) return e;
+    if ((e = convert_in(li, dev_in, d->ilen, dp->is_double, ws->x.p, xs, 0, st))) return e;
+    const size_t ys = (total + 63) & ~size_t(63);
+    if ((e = ws->y.reserve(ys * n_sig * esz))) return e;
+    XView xv{ws->x.p, xs, 0, long(d->ilen), long(d->ilen)};
+    if ((e = run_range(*dp, xv, n_sig, 0, long(total), ws->y.p, ys, ws, st))) return e;
+
+    DitherCfg dc;
+    dc.enabled = d->dtype == B200SOXR_INT16 && !(d->flags & B200SOXR_BATCH_NO_DITHER);
+    dc.split = d->flags & B200SOXR_BATCH_SPLIT_SEMANTICS;
+    unsigned long long bits;
+    std::memcpy(&bits, &io_ratio, 8);
+    dc.seed0 = d->channels ^ bits;                                 // soxr.c:439
+    if (dc.enabled) {
+      CallEmu emu(dp->plan);
+      const size_t cap = size_t(double(d->ilen) * d->out_rate / d->in_rate + 1);   // soxr_ext.cpp:238
+      size_t pos = 0;
+      if (d->flags & B200SOXR_BATCH_EMULATE_CALLS) {
+        const size_t dl = div_len_of(d->in_rate, d->out_rate);
+        for (size_t idx = 0; idx < d->ilen; idx += dl) {
+          const size_t od = emu.process(std::min(dl, d->ilen - idx), cap - pos);
+          dc.call_lens.push_back((long long)od);
+          pos += od;
+        }
+        const size_t od = emu.flush(cap - pos);
+        dc.call_lens.push_back((long long)od);
+        pos += od;
+      } else if (d->flags & B200SOXR_BATCH_ONESHOT_CALLS) {
+        emu.add_input(d->ilen);
+        const size_t od = emu.pull(cap, true);
+        dc.call_lens.push_back((long long)od);
+        pos += od;
+      } else {
+        dc.call_lens.push_back((long long)total);
+        pos = total;
+      }
+      if (pos != total) return "internal: emulated call partition does not cover the output";
+    }
+    if ((e = ws->misc.reserve(8))) return e;
+    B2_CUDA(cudaMemsetAsync(ws->misc.p, 0, 8, st));
+    if ((e = convert_out(lo, dev_out, 0, total, dp->is_double, ws->y.p, ys, dc, ws->misc.as<unsigned long long>(), ws, st)))
+      return e;
+    if (clips && d->dtype >= B200SOXR_INT32) {
+      unsigned long long c = 0;
+      B2_CUDA(cudaMemcpyAsync(&c, ws->misc.p, 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaStreamSynchronize(st));
+      *clips = size_t(c);
+    }
+  }
+  if (!dev_ptrs) {
+    if (out_span) B2_CUDA(cudaMemcpyAsync(out, dev_out, out_span * isz, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+  }
+  return nullptr;
+}
+
+b200soxr_error_t b200soxr_quantize(void const *planar, int is_double, unsigned channels, size_t n,
+                                   size_t const *call_lens, size_t n_calls, int out_dtype, int dither, int split,
+                                   unsigned long long *seed, void *out, size_t *clips) {
+  if (!device_ok()) return kNoDevice;
+  if (out_dtype != B200SOXR_INT16 && out_dtype != B200SOXR_INT32) return "invalid io datatype(s)";
+  Workspace *ws = acquire_workspace();
+  struct Rel { Workspace *w; ~Rel() { release_workspace(w); } } rel{ws};
+  cudaStream_t st = ws->stream;
+  const size_t es = is_double ? 8 : 4, osz = dtype_size(out_dtype);
+  const char *e;
+  if ((e = ws->y.reserve(std::max<size_t>(1, n * channels) * es))) return e;
+  if ((e = ws->out_stage.reserve(std::max<size_t>(1, n * channels) * osz))) return e;
+  if ((e = ws->misc.reserve(16))) return e;
+  B2_CUDA(cudaMemsetAsync(ws->misc.p, 0, 16, st));
+  if (n) B2_CUDA(cudaMemcpyAsync(ws->y.p, planar, n * channels * es, cudaMemcpyHostToDevice, st));
+  IoLayout lay{out_dtype, 1, channels, 0, (long long)channels, 1};
+  DitherCfg dc;
+  dc.enabled = dither && out_dtype == B200SOXR_INT16;
+  dc.split = split;
+  dc.seed0 = seed ? *seed : 0;
+  for (size_t i = 0; i < n_calls; ++i) dc.call_lens.push_back((long long)call_lens[i]);
+  dc.seed_end_dev = ws->misc.as<unsigned long long>() + 1;
+  if ((e = convert_out(lay, ws->out_stage.p, 0, n, is_double, ws->y.p, n, dc, ws->misc.as<unsigned long long>(), ws, st)))
+    return e;
+  unsigned long long host[2] = {0, 0};
+  if (n) B2_CUDA(cudaMemcpyAsync(out, ws->out_stage.p, n * channels * osz, cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaMemcpyAsync(host, ws->misc.p, 16, cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaStreamSynchronize(st));
+  if (clips) *clips = size_t(host[0]);
+  if (seed && dc.enabled) *seed = host[1];
+  return nullptr;
+}
+
+}  // extern "C"

@@ -1,0 +1,288 @@
+// kernels_generic.cuh -- position-keyed stage kernels that work for ANY plan.
+//
+// These are the complete-coverage path: every stage kind the planner can emit
+// runs here as a direct-form kernel over planar signals in HBM.  The hot shapes
+// (DFT stage [+ rational polyphase]) have a fused shared-memory FFT kernel in
+// fft_stage.cuh; both compute the same closed forms (plan.h).
+//
+// Signals are planar: signal s (= clip*channels + channel) occupies
+// buf[s*stride + (k - base)] for logical sample index k.  Reads outside
+// [vlo, vhi) return 0 (zero history before the stream start / flush zeros).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b2 {
+
+template <typename T>
+struct SigIn {
+  const T *p;
+  size_t stride;
+  long base, vlo, vhi;
+  __device__ __forceinline__ T at(unsigned s, long k) const {
+    return (k >= vlo && k < vhi) ? p[size_t(s) * stride + size_t(k - base)] : T(0);
+  }
+};
+template <typename T>
+struct SigOut {
+  T *p;
+  size_t stride;
+  long base;
+  __device__ __forceinline__ T &at(unsigned s, long n) const { return p[size_t(s) * stride + size_t(n - base)]; }
+};
+
+// ---- K1: deinterleave + convert-in (role of data-io.c:13-57: plain C cast, no scaling)
+template <typename Tin, typename T>
+__global__ void k_convert_in(const Tin *__restrict__ in, long long clip_stride, long long frame_stride,
+                             long long chan_stride, unsigned channels, size_t n_frames, unsigned n_sig,
+                             T *__restrict__ X, size_t x_stride, size_t x_off) {
+  const size_t k = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (k >= n_frames) return;
+  for (unsigned s = blockIdx.y; s < n_sig; s += gridDim.y) {
+    const unsigned b = s / channels, c = s % channels;
+    X[size_t(s) * x_stride + x_off + k] = T(in[b * clip_stride + (long long)k * frame_stride + c * chan_stride]);
+  }
+}
+
+// ---- rational stage, direct form:  out[n] = sum_k g[C + M n - L k] in[k]
+// (half-band half-fir.h:38-50, DFT stage cr.c:68-174, vpoly0 poly-fir0.h:24-44)
+template <typename T>
+__global__ void k_rational(SigIn<T> in, const T *__restrict__ g, int n_g, long C, int L, int M,
+                           SigOut<T> out, long o0, long n_out, unsigned n_sig) {
+  const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  const long n = o0 + i, top = C + long(M) * n;
+  long k_hi = top >= 0 ? top / L : -1;
+  const long t = top - (n_g - 1);
+  long k_lo = t <= 0 ? 0 : (t + L - 1) / L;
+  if (k_lo < in.vlo) k_lo = in.vlo;
+  if (k_hi > in.vhi - 1) k_hi = in.vhi - 1;
+  for (unsigned s = blockIdx.y; s < n_sig; s += gridDim.y) {
+    double acc = 0;
+    const T *src = in.p + size_t(s) * in.stride - in.base;
+    for (long k = k_lo; k <= k_hi; ++k) acc = fma(double(g[top - L * k]), double(src[k]), acc);
+    out.at(s, n) = T(acc);
+  }
+}
+
+// ---- interpolated-coefficient polyphase stage (vpoly1..3, poly-fir.h:89-101):
+// 32.32 fixed-point clock; phase = top `phase_bits` of the fraction, x = the rest.
+// table: [phase][tap][order+1], highest order first.
+template <typename T>
+__global__ void k_poly_interp(SigIn<T> in, const T *__restrict__ table, int n_taps, int order,
+                              int phase_bits, unsigned long long at0, unsigned long long step,
+                              int preload, SigOut<T> out, long o0, long n_out, unsigned n_sig) {
+  const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  const long n = o0 + i;
+  const unsigned long long at = at0 + step * (unsigned long long)n;
+  const long pos = long(at >> 32) - preload;
+  const unsigned frac = unsigned(at);
+  const int phase = int(frac >> (32 - phase_bits));
+  const T x = T(double(unsigned(frac << phase_bits)) * (1. / 4294967296.));
+  const T *c = table + size_t(phase) * n_taps * (order + 1);
+  for (unsigned s = blockIdx.y; s < n_sig; s += gridDim.y) {
+    double acc = 0;
+    for (int j = 0; j < n_taps; ++j) {
+      const T *cj = c + j * (order + 1);
+      T v = cj[0];
+      for (int o = 1; o <= order; ++o) v = v * x + cj[o];   // Horner in engine precision, as the reference
+      acc = fma(double(v), double(in.at(s, pos + j)), acc);
+    }
+    out.at(s, n) = T(acc);
+  }
+}
+
+// ---- `quick' cubic stage (QQ), cr-core.c:49-67
+template <typename T>
+__global__ void k_cubic(SigIn<T> in, unsigned long long step, double mult, SigOut<T> out, long o0,
+                        long n_out, unsigned n_sig) {
+  const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  const long n = o0 + i;
+  const unsigned long long at = step * (unsigned long long)n;
+  const long p = long(at >> 32);
+  const double x = double(unsigned(at)) * (1. / 4294967296.);
+  for (unsigned s = blockIdx.y; s < n_sig; s += gridDim.y) {
+    const double s0 = in.at(s, p), s1 = in.at(s, p + 1), s2 = in.at(s, p + 2), sm = in.at(s, p - 1);
+    const double b = .5 * (s1 + sm) - s0, a = (1 / 6.) * (s2 - s1 + sm - s0 - 4 * b), c = s1 - s0 - a - b;
+    out.at(s, n) = T(mult * (((a * x + b) * x + c) * x + s0));
+  }
+}
+
+// ---- K7 (float outputs): interleave + cast (data-io.c:161-170)
+template <typename T, typename Tout>
+__global__ void k_convert_out_float(const T *__restrict__ Y, size_t y_stride, size_t n_frames,
+                                    unsigned channels, unsigned n_sig, Tout *__restrict__ out,
+                                    long long clip_stride, long long frame_stride, long long chan_stride,
+                                    size_t frame_off) {
+  const size_t k = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (k >= n_frames) return;
+  for (unsigned s = blockIdx.y; s < n_sig; s += gridDim.y) {
+    const unsigned b = s / channels, c = s % channels;
+    out[b * clip_stride + (long long)(frame_off + k) * frame_stride + c * chan_stride] = Tout(Y[size_t(s) * y_stride + k]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K7 (integer outputs): round-half-even, saturate + clip count, TPDF dither.
+// Behaviour restated from rint-clip.h as compiled on x86-64 (x87 `fistp`):
+// see SURVEY.md Appendix C.
+// ---------------------------------------------------------------------------
+#define B2_LCG_A 0xd1342543de82ef95ULL
+#define B2_LCG_C 0x6a09e667f3bcc909ULL
+
+__host__ __device__ inline unsigned long long lcg_next(unsigned long long s) { return B2_LCG_A * s + B2_LCG_C; }
+// seed after k LCG steps, O(log k)
+__host__ __device__ inline unsigned long long lcg_jump(unsigned long long s, unsigned long long k) {
+  unsigned long long a = B2_LCG_A, c = B2_LCG_C, ra = 1, rc = 0;
+  while (k) {
+    if (k & 1) { ra = ra * a; rc = rc * a + c; }
+    c = c * a + c;
+    a = a * a;
+    k >>= 1;
+  }
+  return ra * s + rc;
+}
+
+template <typename T> __device__ inline unsigned bits32(T v);
+template <> __device__ inline unsigned bits32<float>(float v) { return __float_as_uint(v); }
+template <> __device__ inline unsigned bits32<double>(double v) { return unsigned(__double_as_longlong(v)); }  // low word
+
+// One block of `n` frames produced by one reference soxr_process call.
+struct DitherBlock { long long start; long long n; };
+
+// Sequential seed pre-pass: one thread per clip walks blocks x channels.
+// seeds[(clip*n_blocks + blk)*channels + ch] = {group-start seed, tail seed (salted, before its 2 steps)}
+template <typename T>
+__global__ void k_dither_seeds(const T *__restrict__ Y, size_t y_stride, unsigned channels, unsigned n_clips,
+                               const DitherBlock *__restrict__ blocks, unsigned n_blocks,
+                               unsigned long long seed0, bool split, ulonglong2 *__restrict__ seeds,
+                               unsigned long long *__restrict__ seed_end) {
+  const unsigned clip = blockIdx.x * blockDim.x + threadIdx.x;
+  if (clip >= n_clips) return;
+  unsigned long long seed = seed0;
+  for (unsigned b = 0; b < n_blocks; ++b) {
+    const long long st = blocks[b].start, n = blocks[b].n;
+    if (!split)  // LSX_RINT_CLIP_2 salts once per call with channel 0 (rint-clip.h:104)
+      seed = seed ^ (unsigned long long)n ^ (n ? bits32<T>(Y[size_t(clip * channels) * y_stride + st + n / 2]) : 0u);
+    for (unsigned c = 0; c < channels; ++c) {
+      const T *src = Y + size_t(clip * channels + c) * y_stride + st;
+      if (split)  // one LSX_RINT_CLIP call per channel (soxr.c:664-677)
+        seed = seed ^ (unsigned long long)n ^ (n ? bits32<T>(src[n / 2]) : 0u);
+      ulonglong2 e;
+      e.x = seed;
+      seed = lcg_jump(seed, 2ull * (unsigned long long)(n / 16));
+      seed = seed ^ (unsigned long long)n ^ (n ? bits32<T>(src[n / 2]) : 0u);   // tail RINT_CLIP re-salt
+      e.y = seed;
+      seed = lcg_next(lcg_next(seed));
+      seeds[(size_t(clip) * n_blocks + b) * channels + c] = e;
+    }
+  }
+  if (seed_end) seed_end[clip] = seed;
+}
+
+template <int BITS> struct IntOf;
+template <> struct IntOf<16> { typedef short type; static constexpr long long vmax = 32767; };
+template <> struct IntOf<32> { typedef int type; static constexpr long long vmax = 2147483647LL; };
+
+// fistp: round to nearest even; out of range / NaN => "invalid" => saturate
+template <int BITS>
+__device__ inline bool rint_sat(double d, typename IntOf<BITS>::type *dst) {
+  const double r = rint(d);
+  const double hi = double(IntOf<BITS>::vmax), lo = -hi - 1;
+  if (!(r >= lo && r <= hi)) {
+    *dst = typename IntOf<BITS>::type(d > 0 ? IntOf<BITS>::vmax : -IntOf<BITS>::vmax - 1);
+    return true;
+  }
+  *dst = typename IntOf<BITS>::type((long long)r);
+  return false;
+}
+
+// One thread per (signal, block, 16-sample group); group index == n/16 is the tail.
+template <typename T, int BITS>
+__global__ void k_rint_clip(const T *__restrict__ Y, size_t y_stride, unsigned channels, unsigned n_sig,
+                            const DitherBlock *__restrict__ blocks, unsigned n_blocks, unsigned max_groups,
+                            const ulonglong2 *__restrict__ seeds /* null: no dither */,
+                            typename IntOf<BITS>::type *__restrict__ out, long long clip_stride,
+                            long long frame_stride, long long chan_stride, long long frame_off,
+                            unsigned long long *__restrict__ clips) {
+  typedef typename IntOf<BITS>::type I;
+  const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned b = blockIdx.y;
+  if (g >= max_groups) return;
+  const long long st = blocks[b].start, n = blocks[b].n;
+  const long long full = n / 16;
+  if (g > full) return;
+  unsigned my_clips = 0;
+  for (unsigned s = blockIdx.z; s < n_sig; s += gridDim.z) {
+    const unsigned clip = s / channels, c = s % channels;
+    const T *src = Y + size_t(s) * y_stride + st;
+    I *dst = out + clip * clip_stride + (frame_off + st) * frame_stride + c * chan_stride;
+    const bool dither = seeds != nullptr;
+    ulonglong2 sd = make_ulonglong2(0, 0);
+    if (dither) sd = seeds[(size_t(clip) * n_blocks + b) * channels + c];
+    if (g < full) {
+      const long long i0 = g * 16;
+      unsigned long long seed1 = 0, ran1 = 0, ran2 = 0;
+      if (dither) {
+        seed1 = lcg_jump(sd.x, 2ull * g);
+        unsigned long long t = lcg_next(seed1);
+        ran1 = t >> 3;
+        t = lcg_next(t);
+        ran2 = t >> 3;
+      }
+      bool invalid = false;
+#pragma unroll 4
+      for (int k = 0; k < 16; ++k) {
+        double d = double(src[i0 + k]);
+        if (dither) {
+          ran1 >>= 3; ran2 >>= 3;
+          d = d + (1. / 32) * double(int((ran1 & 31) - (ran2 & 31)));
+        }
+        I v;
+        invalid |= rint_sat<BITS>(d, &v);
+        dst[(i0 + k) * frame_stride] = v;
+      }
+      if (invalid) {   // group redone by RINT_CLIP from the pre-group seed, re-salted (rint-clip.h:37-54,70-73)
+        const long long ne = i0 + 16;
+        if (dither) {
+          unsigned long long t = seed1 ^ (unsigned long long)ne ^ bits32<T>(src[ne / 2]);
+          t = lcg_next(t); ran1 = t >> 3;
+          t = lcg_next(t); ran2 = t >> 3;
+        }
+        for (int k = 0; k < 16; ++k) {
+          double d = double(src[i0 + k]);
+          if (dither) {
+            ran1 >>= 3; ran2 >>= 3;
+            d = d + (1. / 32) * double(int((ran1 & 31) - (ran2 & 31)));
+          }
+          I v;
+          if (rint_sat<BITS>(d, &v)) ++my_clips;
+          dst[(i0 + k) * frame_stride] = v;
+        }
+      }
+    } else {           // tail: one RINT_CLIP pass with one ran pair (rint-clip.h:75)
+      unsigned long long ran1 = 0, ran2 = 0;
+      if (dither) {
+        unsigned long long t = lcg_next(sd.y);
+        ran1 = t >> 3;
+        t = lcg_next(t);
+        ran2 = t >> 3;
+      }
+      for (long long i = full * 16; i < n; ++i) {
+        double d = double(src[i]);
+        if (dither) {
+          ran1 >>= 3; ran2 >>= 3;
+          d = d + (1. / 32) * double(int((ran1 & 31) - (ran2 & 31)));
+        }
+        I v;
+        if (rint_sat<BITS>(d, &v)) ++my_clips;
+        dst[i * frame_stride] = v;
+      }
+    }
+  }
+  if (my_clips) atomicAdd(clips, (unsigned long long)my_clips);
+}
+
+}  // namespace b2

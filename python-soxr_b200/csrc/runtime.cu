@@ -1,0 +1,375 @@
+// runtime.cu -- plan upload/cache, workspace pool, range executor, dtype conversion.
+#include "runtime.h"
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+
+#include "fft_stage.cuh"
+#include "kernels_generic.cuh"
+
+namespace b2 {
+
+std::atomic<unsigned long long> g_launches{0};
+
+const char *cuda_err(cudaError_t e) {
+  // cudaGetErrorString returns a static string
+  return cudaGetErrorString(e);
+}
+
+const char *DevBuf::reserve(size_t bytes) {
+  if (bytes <= cap) return nullptr;
+  release();
+  size_t want = std::max(bytes, size_t(1) << 16);
+  want = (want + (want >> 2) + 255) & ~size_t(255);   // 25 % head-room
+  B2_CUDA(cudaMalloc(&p, want));
+  cap = want;
+  return nullptr;
+}
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+}
+const char *PinnedBuf::reserve(size_t bytes) {
+  if (bytes <= cap) return nullptr;
+  release();
+  size_t want = std::max(bytes, size_t(1) << 16);
+  want = (want + (want >> 2) + 255) & ~size_t(255);
+  B2_CUDA(cudaMallocHost(&p, want));
+  cap = want;
+  return nullptr;
+}
+void PinnedBuf::release() {
+  if (p) cudaFreeHost(p);
+  p = nullptr;
+  cap = 0;
+}
+
+DevicePlan::~DevicePlan() {
+  for (DevStage &s : stages) { s.g.release(); s.table.release(); s.spec.release(); s.twid.release(); s.ptab.release(); }
+}
+
+Workspace::~Workspace() {
+  for (DevBuf *b : {&in_stage, &out_stage, &x, &y, &t0, &t1, &seeds, &blocks, &misc}) b->release();
+  for (PinnedBuf *b : {&pin_in, &pin_out, &pin_misc}) b->release();
+  if (stream) cudaStreamDestroy(stream);
+}
+
+namespace {
+std::mutex g_ws_mu;
+std::vector<Workspace *> g_ws_free;
+
+template <typename T>
+const char *upload(const std::vector<double> &v, DevBuf *dst) {
+  if (v.empty()) return nullptr;
+  std::vector<T> tmp(v.size());
+  for (size_t i = 0; i < v.size(); ++i) tmp[i] = T(v[i]);
+  if (const char *e = dst->reserve(tmp.size() * sizeof(T))) return e;
+  B2_CUDA(cudaMemcpy(dst->p, tmp.data(), tmp.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return nullptr;
+}
+
+struct PlanKey {
+  unsigned long long ratio_bits, gain_bits;
+  double precision, passband_end, stopband_begin;
+  unsigned long qflags, rflags;
+  unsigned min_dft, large_dft, coef_kb;
+  int device;
+  bool operator<(const PlanKey &o) const { return std::memcmp(this, &o, sizeof *this) < 0; }
+};
+std::mutex g_plan_mu;
+std::map<PlanKey, std::shared_ptr<DevicePlan>> g_plans;
+}  // namespace
+
+Workspace *acquire_workspace() {
+  {
+    std::lock_guard<std::mutex> l(g_ws_mu);
+    if (!g_ws_free.empty()) {
+      Workspace *w = g_ws_free.back();
+      g_ws_free.pop_back();
+      return w;
+    }
+  }
+  Workspace *w = new Workspace();
+  if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess) w->stream = nullptr;
+  return w;
+}
+void release_workspace(Workspace *w) {
+  std::lock_guard<std::mutex> l(g_ws_mu);
+  g_ws_free.push_back(w);
+}
+
+const char *get_device_plan(double io_ratio, const QSpec &q, const RSpec &r, double multiplier,
+                            std::shared_ptr<DevicePlan> *out) {
+  PlanKey key;
+  std::memset(&key, 0, sizeof key);
+  std::memcpy(&key.ratio_bits, &io_ratio, 8);
+  std::memcpy(&key.gain_bits, &multiplier, 8);
+  key.precision = q.precision;
+  key.passband_end = q.passband_end;
+  key.stopband_begin = q.stopband_begin;
+  key.qflags = q.flags;
+  key.rflags = r.flags & 0xff;
+  key.min_dft = r.log2_min_dft_size;
+  key.large_dft = r.log2_large_dft_size;
+  key.coef_kb = r.coef_size_kbytes;
+  int dev = 0;
+  B2_CUDA(cudaGetDevice(&dev));
+  key.device = dev;
+  std::lock_guard<std::mutex> l(g_plan_mu);
+  auto it = g_plans.find(key);
+  if (it != g_plans.end()) { *out = it->second; return nullptr; }
+  auto dp = std::make_shared<DevicePlan>();
+  if (const char *e = make_plan(io_ratio, q, r, multiplier, &dp->plan)) return e;
+  dp->is_double = dp->plan.is_double;
+  dp->stages.resize(dp->plan.stages.size());
+  for (size_t i = 0; i < dp->plan.stages.size(); ++i) {
+    const Stage &s = dp->plan.stages[i];
+    DevStage &d = dp->stages[i];
+    const char *e = nullptr;
+    if (dp->is_double) {
+      e = upload<double>(s.g, &d.g);
+      if (!e && s.kind == kPolyInterp) e = upload<double>(s.table, &d.table);
+    } else {
+      e = upload<float>(s.g, &d.g);
+      if (!e && s.kind == kPolyInterp) e = upload<float>(s.table, &d.table);
+    }
+    if (e) return e;
+  }
+  if (const char *e = fft_stage_prepare(dp.get())) return e;
+  g_plans[key] = dp;
+  *out = dp;
+  return nullptr;
+}
+
+// ---------------------------------------------------------------------------
+
+namespace {
+inline dim3 grid_for(size_t n, unsigned n_sig, unsigned threads = 256) {
+  return dim3(unsigned((n + threads - 1) / threads), std::min(n_sig, 65535u), 1);
+}
+
+template <typename Tin, typename T>
+const char *convert_in_t(const IoLayout &lay, const void *in, size_t n_frames, T *X, size_t xs, size_t xo,
+                         cudaStream_t st) {
+  const unsigned n_sig = lay.n_clips * lay.channels;
+  if (!n_frames || !n_sig) return nullptr;
+  k_convert_in<Tin, T><<<grid_for(n_frames, n_sig), 256, 0, st>>>(
+      static_cast<const Tin *>(in), lay.clip_stride, lay.frame_stride, lay.chan_stride, lay.channels, n_frames,
+      n_sig, X, xs, xo);
+  B2_COUNT_LAUNCH();
+  B2_CUDA(cudaGetLastError());
+  return nullptr;
+}
+template <typename T>
+const char *convert_in_d(const IoLayout &lay, const void *in, size_t n, void *X, size_t xs, size_t xo, cudaStream_t st) {
+  switch (lay.dtype) {
+    case 0: return convert_in_t<float, T>(lay, in, n, static_cast<T *>(X), xs, xo, st);
+    case 1: return convert_in_t<double, T>(lay, in, n, static_cast<T *>(X), xs, xo, st);
+    case 2: return convert_in_t<int, T>(lay, in, n, static_cast<T *>(X), xs, xo, st);
+    case 3: return convert_in_t<short, T>(lay, in, n, static_cast<T *>(X), xs, xo, st);
+  }
+  return "invalid io datatype(s)";
+}
+}  // namespace
+
+const char *convert_in(const IoLayout &lay, const void *dev_in, size_t n_frames, bool is_double, void *X,
+                       size_t x_stride, size_t x_off, cudaStream_t stream) {
+  return is_double ? convert_in_d<double>(lay, dev_in, n_frames, X, x_stride, x_off, stream)
+                   : convert_in_d<float>(lay, dev_in, n_frames, X, x_stride, x_off, stream);
+}
+
+namespace {
+template <typename T, int BITS>
+const char *convert_out_int(const IoLayout &lay, void *out, size_t frame_off, size_t n_frames, const T *Y,
+                            size_t ys, const DitherCfg &dc, unsigned long long *clips_dev, Workspace *ws,
+                            cudaStream_t st) {
+  const unsigned n_sig = lay.n_clips * lay.channels;
+  // block partition (one block == one reference soxr_process call)
+  std::vector<DitherBlock> blocks;
+  if (dc.enabled && !dc.call_lens.empty()) {
+    long long pos = 0;
+    for (long long n : dc.call_lens) { blocks.push_back({pos, n}); pos += n; }
+  } else {
+    blocks.push_back({0, (long long)n_frames});
+  }
+  const unsigned nb = unsigned(blocks.size());
+  long long max_n = 0;
+  for (auto &b : blocks) max_n = std::max(max_n, b.n);
+  if (const char *e = ws->blocks.reserve(nb * sizeof(DitherBlock))) return e;
+  if (const char *e = ws->pin_misc.reserve(nb * sizeof(DitherBlock))) return e;
+  std::memcpy(ws->pin_misc.p, blocks.data(), nb * sizeof(DitherBlock));
+  B2_CUDA(cudaMemcpyAsync(ws->blocks.p, ws->pin_misc.p, nb * sizeof(DitherBlock), cudaMemcpyHostToDevice, st));
+  ulonglong2 *seeds = nullptr;
+  if (dc.enabled) {
+    if (const char *e = ws->seeds.reserve(size_t(lay.n_clips) * nb * lay.channels * sizeof(ulonglong2))) return e;
+    seeds = ws->seeds.as<ulonglong2>();
+    k_dither_seeds<T><<<(lay.n_clips + 63) / 64, 64, 0, st>>>(Y, ys, lay.channels, lay.n_clips,
+                                                            ws->blocks.as<DitherBlock>(), nb, dc.seed0, dc.split,
+                                                            seeds, dc.seed_end_dev);
+    B2_COUNT_LAUNCH();
+    B2_CUDA(cudaGetLastError());
+  }
+  if (n_sig && nb) {
+    const unsigned max_groups = unsigned(max_n / 16 + 1);
+    dim3 grid((max_groups + 127) / 128, nb, std::min(n_sig, 65535u));
+    if (grid.y > 65535) return "too many dither blocks";
+    k_rint_clip<T, BITS><<<grid, 128, 0, st>>>(Y, ys, lay.channels, n_sig, ws->blocks.as<DitherBlock>(), nb,
+                                                max_groups, seeds, static_cast<typename IntOf<BITS>::type *>(out),
+                                                lay.clip_stride, lay.frame_stride, lay.chan_stride,
+                                                (long long)frame_off, clips_dev);
+    B2_COUNT_LAUNCH();
+    B2_CUDA(cudaGetLastError());
+  }
+  return nullptr;
+}
+
+template <typename T>
+const char *convert_out_t(const IoLayout &lay, void *out, size_t frame_off, size_t n_frames, const T *Y,
+                          size_t ys, const DitherCfg &dc, unsigned long long *clips_dev, Workspace *ws,
+                          cudaStream_t st) {
+  const unsigned n_sig = lay.n_clips * lay.channels;
+  switch (lay.dtype) {
+    case 0:
+    case 1:
+      if (!n_frames || !n_sig) return nullptr;
+      if (lay.dtype == 0)
+        k_convert_out_float<T, float><<<grid_for(n_frames, n_sig), 256, 0, st>>>(
+            Y, ys, n_frames, lay.channels, n_sig, static_cast<float *>(out), lay.clip_stride, lay.frame_stride,
+            lay.chan_stride, frame_off);
+      else
+        k_convert_out_float<T, double><<<grid_for(n_frames, n_sig), 256, 0, st>>>(
+            Y, ys, n_frames, lay.channels, n_sig, static_cast<double *>(out), lay.clip_stride, lay.frame_stride,
+            lay.chan_stride, frame_off);
+      B2_COUNT_LAUNCH();
+      B2_CUDA(cudaGetLastError());
+      return nullptr;
+    case 2: {
+      DitherCfg nd;   // int32 is never dithered (data-io.c:207-209)
+      return convert_out_int<T, 32>(lay, out, frame_off, n_frames, Y, ys, nd, clips_dev, ws, st);
+    }
+    case 3: return convert_out_int<T, 16>(lay, out, frame_off, n_frames, Y, ys, dc, clips_dev, ws, st);
+  }
+  return "invalid io datatype(s)";
+}
+}  // namespace
+
+const char *convert_out(const IoLayout &lay, void *dev_out, size_t frame_off, size_t n_frames, bool is_double,
+                        const void *Y, size_t y_stride, const DitherCfg &dc, unsigned long long *clips_dev,
+                        Workspace *ws, cudaStream_t stream) {
+  return is_double ? convert_out_t<double>(lay, dev_out, frame_off, n_frames, static_cast<const double *>(Y),
+                                           y_stride, dc, clips_dev, ws, stream)
+                   : convert_out_t<float>(lay, dev_out, frame_off, n_frames, static_cast<const float *>(Y),
+                                          y_stride, dc, clips_dev, ws, stream);
+}
+
+// ---------------------------------------------------------------------------
+// Range executor
+// ---------------------------------------------------------------------------
+
+namespace {
+
+struct Range { long lo, hi; };
+
+// Output range of stage s-1 needed to produce outputs [r.lo, r.hi) of stage s.
+Range input_range(const DevicePlan &dp, size_t s, Range r) {
+  const Stage &st = dp.plan.stages[s];
+  if (r.hi <= r.lo) return {0, 0};
+  Range need{stage_input_first(st, r.lo), stage_input_needed(st, r.hi)};
+  if (dp.fft && dp.fft->stage_index == int(s)) need = fft_stage_input_range(*dp.fft, st, r);
+  need.lo = std::max(need.lo, 0L);
+  need.hi = std::max(need.hi, need.lo);
+  return need;
+}
+
+template <typename T>
+const char *run_stage_generic(const DevicePlan &dp, size_t si, SigIn<T> in, SigOut<T> out, Range r,
+                              unsigned n_sig, cudaStream_t st) {
+  const Stage &s = dp.plan.stages[si];
+  const DevStage &d = dp.stages[si];
+  const long n_out = r.hi - r.lo;
+  if (n_out <= 0 || !n_sig) return nullptr;
+  const dim3 grid = grid_for(size_t(n_out), n_sig, 128);
+  switch (s.kind) {
+    case kHalf: case kDft: case kPoly:
+      k_rational<T><<<grid, 128, 0, st>>>(in, d.g.as<T>(), int(s.g.size()), s.C, s.L, s.M, out, r.lo, n_out, n_sig);
+      break;
+    case kPolyInterp:
+      k_poly_interp<T><<<grid, 128, 0, st>>>(in, d.table.as<T>(), s.num_coefs, s.order, s.phase_bits, s.at0_fix,
+                                             s.step_fix, s.dev_preload, out, r.lo, n_out, n_sig);
+      break;
+    case kCubic:
+      k_cubic<T><<<grid, 128, 0, st>>>(in, s.step_fix, s.cubic_mult, out, r.lo, n_out, n_sig);
+      break;
+  }
+  B2_COUNT_LAUNCH();
+  B2_CUDA(cudaGetLastError());
+  return nullptr;
+}
+
+template <typename T>
+const char *run_range_t(const DevicePlan &dp, const XView &x, unsigned n_sig, long o0, long o1, T *Y,
+                        size_t y_stride, Workspace *ws, cudaStream_t st) {
+  const size_t S = dp.plan.stages.size();
+  if (o1 <= o0 || !n_sig) return nullptr;
+  const long x_vhi = x.n_in_total >= 0 ? std::min(x.hi, x.n_in_total) : x.hi;
+  if (S == 0) {   // unity ratio: samples pass through (cr.c:347; zero-extended by flush)
+    B2_CUDA(cudaMemsetAsync(Y, 0, size_t(n_sig) * y_stride * sizeof(T), st));
+    const long lo = std::max(o0, x.base), hi = std::min(o1, x_vhi);
+    if (hi > lo)
+      B2_CUDA(cudaMemcpy2DAsync(Y + (lo - o0), y_stride * sizeof(T),
+                                static_cast<const T *>(x.p) + (lo - x.base), x.stride * sizeof(T),
+                                size_t(hi - lo) * sizeof(T), n_sig, cudaMemcpyDeviceToDevice, st));
+    return nullptr;
+  }
+  // ranges back to front
+  std::vector<Range> out_r(S);
+  out_r[S - 1] = {o0, o1};
+  for (size_t s = S - 1; s > 0; --s) out_r[s - 1] = input_range(dp, s, out_r[s]);
+  const Range xin = input_range(dp, 0, out_r[0]);
+  if (xin.hi > xin.lo && xin.lo < x.base) return "internal: input history trimmed too far";
+  if (x.n_in_total < 0 && xin.hi > x.hi) return "internal: output range needs input that has not arrived";
+
+  SigIn<T> in{static_cast<const T *>(x.p), x.stride, x.base, std::max(0L, x.base), x_vhi};
+  DevBuf *in_buf = nullptr;   // which scratch buffer `in` lives in (nullptr: the caller's X)
+  for (size_t s = 0; s < S; ++s) {
+    const bool use_fft = dp.fft && dp.fft->stage_index == int(s);
+    const size_t last = (use_fft && dp.fft->fused_poly) ? s + 1 : s;   // last stage covered by this launch
+    const Range r = out_r[last];
+    const size_t len = size_t(std::max(0L, r.hi - r.lo));
+    SigOut<T> out;
+    DevBuf *out_buf = nullptr;
+    if (last + 1 == S) out = SigOut<T>{Y, y_stride, o0};
+    else {
+      out_buf = (in_buf == &ws->t0) ? &ws->t1 : &ws->t0;
+      const size_t stride = (len + 63) & ~size_t(63);
+      if (const char *e = out_buf->reserve(std::max<size_t>(1, stride * n_sig) * sizeof(T))) return e;
+      out = SigOut<T>{out_buf->as<T>(), stride, r.lo};
+    }
+    const char *e = use_fft ? fft_stage_run<T>(dp, *dp.fft, in.p, in.stride, in.base, in.vlo, in.vhi, out.p,
+                                               out.stride, out.base, r.lo, r.hi, n_sig, st)
+                            : run_stage_generic<T>(dp, s, in, out, r, n_sig, st);
+    if (e) return e;
+    s = last;
+    // intermediate signals exist for index >= 0 only (FIFO preloads are zeros, cr.c:487-490)
+    in = SigIn<T>{out.p, out.stride, out.base, std::max(0L, r.lo), r.hi};
+    in_buf = out_buf;
+  }
+  return nullptr;
+}
+}  // namespace
+
+const char *run_range(const DevicePlan &dp, const XView &x, unsigned n_sig, long o0, long o1, void *Y,
+                      size_t y_stride, Workspace *ws, cudaStream_t stream) {
+  return dp.is_double ? run_range_t<double>(dp, x, n_sig, o0, o1, static_cast<double *>(Y), y_stride, ws, stream)
+                      : run_range_t<float>(dp, x, n_sig, o0, o1, static_cast<float *>(Y), y_stride, ws, stream);
+}
+
+long history_needed_from(const DevicePlan &dp, long o) {
+  Range r{o, o + 1};
+  for (size_t s = dp.plan.stages.size(); s-- > 0;) r = input_range(dp, s, r);
+  return r.lo;
+}
+
+}  // namespace b2

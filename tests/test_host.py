@@ -1,0 +1,116 @@
+"""CPU tests of the product's host side: C-ABI symbols, planner vs the reference's
+SOXR_TRACE plans, call-schedule emulation vs the reference's stream patterns,
+front-end argument validation.  No compute call is made (no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from _golden import Q, load_plans, load_streams
+
+import soxr
+from soxr import soxr_ext
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PLANS = load_plans()
+STREAMS = load_streams()
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "b200soxr.h")).read()
+    names = set(re.findall(r"\b(b200soxr_[a-z_0-9]+)\s*\(", hdr))
+    assert len(names) >= 18
+    lib = C.CDLL(os.path.join(ROOT, "python-soxr_b200", "soxr", "libb200soxr.so"))
+    for n in sorted(names):
+        assert hasattr(lib, n), n
+
+
+def test_spec_constructors_match_reference_presets():
+    # soxr.c:106-145: HQ -> 20 bit, VHQ -> 28 bit, Fp0 values from SURVEY.md section 8a-R1
+    lib = soxr_ext._lib
+    hq = lib.b200soxr_quality_spec(soxr.HQ, 0)
+    vhq = lib.b200soxr_quality_spec(soxr.VHQ, 0)
+    assert (hq.precision, vhq.precision) == (20, 28)
+    assert hq.phase_response == 50 and hq.stopband_begin == 1
+    assert abs(hq.passband_end - 0.913744) < 1e-6 and abs(vhq.passband_end - 0.911328) < 1e-6
+    rt = lib.b200soxr_runtime_spec(1)
+    assert (rt.log2_min_dft_size, rt.log2_large_dft_size, rt.coef_size_kbytes) == (10, 17, 400)
+    io = lib.b200soxr_io_spec(3, 3)
+    assert io.scale == 1 and not io.e
+    assert lib.b200soxr_io_spec(9, 0).e
+
+
+@pytest.mark.parametrize("key", sorted(PLANS))
+def test_planner_matches_reference_trace(key):
+    i, o, q = key.split(":")
+    assert soxr_ext.plan_dump(float(i), float(o), Q[q]) == PLANS[key]
+
+
+@pytest.mark.parametrize("name", sorted(STREAMS))
+def test_call_emulation_matches_reference_stream(name):
+    s = STREAMS[name]
+    n, chunk = s['frames'], s['chunk']
+    lens = [min(chunk, n - i) for i in range(0, n, chunk)]
+    # every chunk but the last is a plain process() call
+    od, dl = soxr_ext.emulate_calls(s['in_rate'], s['out_rate'], Q[s['quality']], lens[:-1])
+    assert od == s['counts'][:-1]
+    assert np.allclose(dl, s['delays'][:-1], rtol=0, atol=1e-9)
+    # the last chunk is followed by flush calls until empty: total must be floor(n*out/in+.5)
+    od2, _ = soxr_ext.emulate_calls(s['in_rate'], s['out_rate'], Q[s['quality']], lens + [0, 0])
+    assert od2[-1] == 0
+    assert sum(od2) == soxr_ext.output_frames(s['in_rate'], s['out_rate'], n)
+    assert od2[-3] + od2[-2] == s['counts'][-1]
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 99, 100, 101, 31999, 32000, 32001, 266151])
+@pytest.mark.parametrize("rates", [(44100, 32000), (32000, 44100), (48000, 44100), (44100, 47999.5)])
+def test_output_frames(n, rates):
+    assert soxr_ext.output_frames(rates[0], rates[1], n) == int(n / (rates[0] / rates[1]) + .5)
+
+
+@pytest.mark.parametrize('in_rate, out_rate', [(100, 0), (50, -1), (0, 100.5), (-1.5, 100)])
+def test_bad_sr(in_rate, out_rate):
+    with pytest.raises(ValueError):
+        soxr.resample(np.zeros(100), in_rate, out_rate)
+    with pytest.raises(ValueError):
+        soxr.ResampleStream(in_rate, out_rate, 1)
+
+
+@pytest.mark.parametrize('dtype', [np.complex64, np.complex128, np.int8, np.int64])
+def test_bad_dtype(dtype):
+    with pytest.raises((TypeError, ValueError)):
+        soxr.resample(np.zeros(100, dtype=dtype), 100, 200)
+    with pytest.raises(TypeError):
+        soxr.ResampleStream(100, 200, 1, dtype=dtype)
+
+
+def test_bad_quality_channels_ndim():
+    with pytest.raises(ValueError):
+        soxr.resample(np.zeros(100, np.float32), 100, 200, quality='ultra')
+    with pytest.raises(ValueError):
+        soxr.resample(np.zeros((4, 4, 4), np.float32), 100, 200)
+    with pytest.raises(ValueError):
+        soxr.ResampleStream(100, 200, 0)
+    with pytest.raises(ValueError):
+        soxr.ResampleStream(100, 200, 65537)
+    assert soxr._quality_to_enum('SOXR_MQ') == soxr.MQ and soxr._quality_to_enum(soxr.VHQ) == soxr.VHQ
+
+
+def test_no_cpu_fallback_without_gpu():
+    if soxr_ext.device_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no usable CUDA device"):
+        soxr.resample(np.zeros(100, np.float32), 48000, 44100)
+    with pytest.raises(RuntimeError, match="no usable CUDA device"):
+        soxr.ResampleStream(48000, 44100, 1)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "python-soxr_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "soxr_oracle" not in txt and "ref_soxr" not in txt and "libsoxr_ref" not in txt, f
