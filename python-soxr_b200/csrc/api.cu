@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -59,6 +60,21 @@ RSpec to_rspec(const b200soxr_runtime_spec_t *r) {
   return s;
 }
 const double kFullScale[] = {1, 1, 65536. * 32768, 32768};   // soxr.c:377
+
+// Arithmetic type of the device path.  The reference runs every recipe above 20 bits in
+// its f64 engine (soxr.c:447) whatever the I/O type.  With float32 in AND out the result is
+// rounded to 24 bits anyway, so the f32 path (measured ~2e-7 RMS from the f64 engine on
+// unit-variance noise, inside the 1e-6 parity budget) is used unless the caller asked for
+// SOXR_DOUBLE_PRECISION or B200SOXR_STRICT_ENGINE=1 is set.  The filters are always the
+// reference's for the recipe.
+bool arith_double_for(const QSpec &q, int itype, int otype) {
+  const bool ref_double = !(q.precision <= 20 && !(q.flags & B200SOXR_DOUBLE_PRECISION));
+  if (!ref_double) return false;
+  if ((itype & 3) != B200SOXR_FLOAT32 || (otype & 3) != B200SOXR_FLOAT32) return true;
+  if (q.flags & B200SOXR_DOUBLE_PRECISION) return true;
+  static const bool strict = [] { const char *e = std::getenv("B200SOXR_STRICT_ENGINE"); return e && e[0] == '1'; }();
+  return strict;
+}
 
 size_t div_len_of(double in_rate, double out_rate) {          // soxr_ext.cpp:71,239
   return size_t(std::max(1000., 48000 * in_rate / out_rate));
@@ -244,7 +260,7 @@ b200soxr_t b200soxr_create(double input_rate, double output_rate, unsigned num_c
     unsigned long long bits;
     std::memcpy(&bits, &io_ratio, 8);
     p->seed = num_channels ^ bits;
-    if (!error) error = get_device_plan(io_ratio, p->q, p->r, scale, &p->dp);
+    if (!error) error = get_device_plan(io_ratio, p->q, p->r, scale, arith_double_for(p->q, p->io.itype, p->io.otype), &p->dp);
     if (!error) {
       p->ws = acquire_workspace();
       p->stream = (rt_spec && rt_spec->e) ? static_cast<cudaStream_t>(rt_spec->e) : p->ws->stream;
@@ -261,7 +277,7 @@ b200soxr_t b200soxr_create(double input_rate, double output_rate, unsigned num_c
 
 double b200soxr_delay(b200soxr_t p) { return (p && !p->error && p->emu) ? p->emu->delay() : 0; }
 size_t *b200soxr_num_clips(b200soxr_t p) { return &p->clips; }
-char const *b200soxr_engine(b200soxr_t p) { return p->dp->plan.engine; }
+char const *b200soxr_engine(b200soxr_t p) { return p->dp->is_double ? "b200-cr64" : "b200-cr32"; }
 
 b200soxr_error_t b200soxr_clear(b200soxr_t p) {
   if (!p) return "invalid soxr_t pointer";
@@ -331,15 +347,9 @@ b200soxr_error_t b200soxr_process(b200soxr_t p, void const *in, size_t ilen0, si
 
   // ---- output (soxr.c:664-733): how much the reference would return now
   const size_t odone = p->emu->pull(olen, p->flushing);
+  const bool int_out = ot >= B200SOXR_INT32;
   if (odone || (ot == B200SOXR_INT16 && !(p->io.flags & B200SOXR_NO_DITHER))) {
     const size_t es = p->esz(), osz = dtype_size(ot);
-    const size_t ys = (std::max<size_t>(odone, 1) + 63) & ~size_t(63);
-    if ((e = ws->y.reserve(ys * ch * es))) return p->error = e;
-    if (odone) {
-      XView xv{p->xbuf.p, p->x_cap, p->x_base, p->x_hi, p->n_in_total};
-      if ((e = run_range(*p->dp, xv, ch, p->out_done, p->out_done + long(odone), ws->y.p, ys, ws, st)))
-        return p->error = e;
-    }
     IoLayout lay;
     lay.dtype = ot;
     lay.n_clips = 1;
@@ -352,15 +362,34 @@ b200soxr_error_t b200soxr_process(b200soxr_t p, void const *in, size_t ilen0, si
       if (split) { lay.frame_stride = 1; lay.chan_stride = (long long)odone; }
       else { lay.frame_stride = ch; lay.chan_stride = 1; }
     }
-    DitherCfg dc;
-    dc.enabled = ot == B200SOXR_INT16 && !(p->io.flags & B200SOXR_NO_DITHER);
-    dc.split = split;
-    dc.seed0 = p->seed;
-    dc.call_lens.push_back((long long)odone);
-    dc.seed_end_dev = p->seed_dev.as<unsigned long long>();
-    if ((e = convert_out(lay, dev_out, 0, odone, p->dp->is_double, ws->y.p, ys, dc, p->clips_dev.as<unsigned long long>(),
-                         ws, st)))
-      return p->error = e;
+    const SigDesc xin = planar_desc(p->xbuf.p, p->dp->is_double, p->x_cap, p->x_base, std::max(0L, p->x_base), p->x_hi);
+    if (!int_out) {
+      // float output: the last launch writes the caller's layout directly (K7 fused)
+      if (odone) {
+        SigDesc od;
+        od.p = dev_out; od.dtype = ot; od.channels = ch; od.clip_stride = 0;
+        od.frame_stride = lay.frame_stride; od.chan_stride = lay.chan_stride; od.base = p->out_done;
+        if ((e = run_range(*p->dp, xin, p->n_in_total, ch, p->out_done, p->out_done + long(odone), od, ws, st)))
+          return p->error = e;
+      }
+    } else {
+      const size_t ys = (std::max<size_t>(odone, 1) + 63) & ~size_t(63);
+      if ((e = ws->y.reserve(ys * ch * es))) return p->error = e;
+      if (odone) {
+        const SigDesc yd = planar_desc(ws->y.p, p->dp->is_double, ys, p->out_done, 0, 0);
+        if ((e = run_range(*p->dp, xin, p->n_in_total, ch, p->out_done, p->out_done + long(odone), yd, ws, st)))
+          return p->error = e;
+      }
+      DitherCfg dc;
+      dc.enabled = ot == B200SOXR_INT16 && !(p->io.flags & B200SOXR_NO_DITHER);
+      dc.split = split;
+      dc.seed0 = p->seed;
+      dc.call_lens.push_back((long long)odone);
+      dc.seed_end_dev = p->seed_dev.as<unsigned long long>();
+      if ((e = convert_out(lay, dev_out, 0, odone, p->dp->is_double, ws->y.p, ys, dc, p->clips_dev.as<unsigned long long>(),
+                           ws, st)))
+        return p->error = e;
+    }
     if (!p->device_io && odone) {
       if (split) {
         void *const *ptrs = static_cast<void *const *>(out);
@@ -370,13 +399,14 @@ b200soxr_error_t b200soxr_process(b200soxr_t p, void const *in, size_t ilen0, si
       } else
         B2_CUDA(cudaMemcpyAsync(out, dev_out, odone * ch * osz, cudaMemcpyDeviceToHost, st));
     }
-    if (ot >= B200SOXR_INT32) {
+    if (int_out) {
       unsigned long long host[2] = {0, 0};
       B2_CUDA(cudaMemcpyAsync(&host[0], p->clips_dev.p, 8, cudaMemcpyDeviceToHost, st));
-      if (dc.enabled) B2_CUDA(cudaMemcpyAsync(&host[1], p->seed_dev.p, 8, cudaMemcpyDeviceToHost, st));
+      const bool dith = ot == B200SOXR_INT16 && !(p->io.flags & B200SOXR_NO_DITHER);
+      if (dith) B2_CUDA(cudaMemcpyAsync(&host[1], p->seed_dev.p, 8, cudaMemcpyDeviceToHost, st));
       B2_CUDA(cudaStreamSynchronize(st));
       p->clips = size_t(host[0]);
-      if (dc.enabled) p->seed = host[1];
+      if (dith) p->seed = host[1];
     }
   }
   if (!p->device_io) B2_CUDA(cudaStreamSynchronize(st));
@@ -417,7 +447,7 @@ b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *d, void co
   const double io_ratio = d->in_rate / d->out_rate;
   const QSpec q = quality_spec(d->quality, (d->flags & B200SOXR_BATCH_DOUBLE) ? B200SOXR_DOUBLE_PRECISION : 0);
   std::shared_ptr<DevicePlan> dp;
-  if (const char *e = get_device_plan(io_ratio, q, RSpec(), 1.0, &dp)) return e;
+  if (const char *e = get_device_plan(io_ratio, q, RSpec(), 1.0, arith_double_for(q, d->dtype, d->dtype), &dp)) return e;
   const size_t total = output_frames(io_ratio, d->ilen);
   if (odone) *odone = total;
   if (clips) *clips = 0;
@@ -450,55 +480,64 @@ b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *d, void co
     dev_out = ws->out_stage.p;
   }
   if (total) {
-    // planar engine-precision input
-    const size_t xs = (std::max<size_t>(d->ilen, 1) + 63) & ~size_t(63);
-    if ((e = ws->x.reserve(xs * n_sig * esz))) return e;
-    if ((e = convert_in(li, dev_in, d->ilen, dp->is_double, ws->x.p, xs, 0, st))) return e;
-    const size_t ys = (total + 63) & ~size_t(63);
-    if ((e = ws->y.reserve(ys * n_sig * esz))) return e;
-    XView xv{ws->x.p, xs, 0, long(d->ilen), long(d->ilen)};
-    if ((e = run_range(*dp, xv, n_sig, 0, long(total), ws->y.p, ys, ws, st))) return e;
+    // the first / last launches read and write the caller's layout directly (K1 / float K7 fused)
+    SigDesc xin;
+    xin.p = const_cast<void *>(dev_in); xin.dtype = d->dtype; xin.channels = d->channels;
+    xin.clip_stride = d->in_clip_stride; xin.frame_stride = d->in_frame_stride; xin.chan_stride = d->in_chan_stride;
+    xin.base = 0; xin.vlo = 0; xin.vhi = long(d->ilen);
+    if (d->dtype <= B200SOXR_FLOAT64) {
+      SigDesc od;
+      od.p = dev_out; od.dtype = d->dtype; od.channels = d->channels;
+      od.clip_stride = d->out_clip_stride; od.frame_stride = d->out_frame_stride; od.chan_stride = d->out_chan_stride;
+      od.base = 0;
+      if ((e = run_range(*dp, xin, long(d->ilen), n_sig, 0, long(total), od, ws, st))) return e;
+    } else {
+      const size_t ys = (total + 63) & ~size_t(63);
+      if ((e = ws->y.reserve(ys * n_sig * esz))) return e;
+      const SigDesc yd = planar_desc(ws->y.p, dp->is_double, ys, 0, 0, 0);
+      if ((e = run_range(*dp, xin, long(d->ilen), n_sig, 0, long(total), yd, ws, st))) return e;
 
-    DitherCfg dc;
-    dc.enabled = d->dtype == B200SOXR_INT16 && !(d->flags & B200SOXR_BATCH_NO_DITHER);
-    dc.split = d->flags & B200SOXR_BATCH_SPLIT_SEMANTICS;
-    unsigned long long bits;
-    std::memcpy(&bits, &io_ratio, 8);
-    dc.seed0 = d->channels ^ bits;                                 // soxr.c:439
-    if (dc.enabled) {
-      CallEmu emu(dp->plan);
-      const size_t cap = size_t(double(d->ilen) * d->out_rate / d->in_rate + 1);   // soxr_ext.cpp:238
-      size_t pos = 0;
-      if (d->flags & B200SOXR_BATCH_EMULATE_CALLS) {
-        const size_t dl = div_len_of(d->in_rate, d->out_rate);
-        for (size_t idx = 0; idx < d->ilen; idx += dl) {
-          const size_t od = emu.process(std::min(dl, d->ilen - idx), cap - pos);
+      DitherCfg dc;
+      dc.enabled = d->dtype == B200SOXR_INT16 && !(d->flags & B200SOXR_BATCH_NO_DITHER);
+      dc.split = d->flags & B200SOXR_BATCH_SPLIT_SEMANTICS;
+      unsigned long long bits;
+      std::memcpy(&bits, &io_ratio, 8);
+      dc.seed0 = d->channels ^ bits;                                 // soxr.c:439
+      if (dc.enabled) {
+        CallEmu emu(dp->plan);
+        const size_t cap = size_t(double(d->ilen) * d->out_rate / d->in_rate + 1);   // soxr_ext.cpp:238
+        size_t pos = 0;
+        if (d->flags & B200SOXR_BATCH_EMULATE_CALLS) {
+          const size_t dl = div_len_of(d->in_rate, d->out_rate);
+          for (size_t idx = 0; idx < d->ilen; idx += dl) {
+            const size_t od = emu.process(std::min(dl, d->ilen - idx), cap - pos);
+            dc.call_lens.push_back((long long)od);
+            pos += od;
+          }
+          const size_t od = emu.flush(cap - pos);
           dc.call_lens.push_back((long long)od);
           pos += od;
+        } else if (d->flags & B200SOXR_BATCH_ONESHOT_CALLS) {
+          emu.add_input(d->ilen);
+          const size_t od = emu.pull(cap, true);
+          dc.call_lens.push_back((long long)od);
+          pos += od;
+        } else {
+          dc.call_lens.push_back((long long)total);
+          pos = total;
         }
-        const size_t od = emu.flush(cap - pos);
-        dc.call_lens.push_back((long long)od);
-        pos += od;
-      } else if (d->flags & B200SOXR_BATCH_ONESHOT_CALLS) {
-        emu.add_input(d->ilen);
-        const size_t od = emu.pull(cap, true);
-        dc.call_lens.push_back((long long)od);
-        pos += od;
-      } else {
-        dc.call_lens.push_back((long long)total);
-        pos = total;
+        if (pos != total) return "internal: emulated call partition does not cover the output";
       }
-      if (pos != total) return "internal: emulated call partition does not cover the output";
-    }
-    if ((e = ws->misc.reserve(8))) return e;
-    B2_CUDA(cudaMemsetAsync(ws->misc.p, 0, 8, st));
-    if ((e = convert_out(lo, dev_out, 0, total, dp->is_double, ws->y.p, ys, dc, ws->misc.as<unsigned long long>(), ws, st)))
-      return e;
-    if (clips && d->dtype >= B200SOXR_INT32) {
-      unsigned long long c = 0;
-      B2_CUDA(cudaMemcpyAsync(&c, ws->misc.p, 8, cudaMemcpyDeviceToHost, st));
-      B2_CUDA(cudaStreamSynchronize(st));
-      *clips = size_t(c);
+      if ((e = ws->misc.reserve(8))) return e;
+      B2_CUDA(cudaMemsetAsync(ws->misc.p, 0, 8, st));
+      if ((e = convert_out(lo, dev_out, 0, total, dp->is_double, ws->y.p, ys, dc, ws->misc.as<unsigned long long>(), ws, st)))
+        return e;
+      if (clips) {
+        unsigned long long c = 0;
+        B2_CUDA(cudaMemcpyAsync(&c, ws->misc.p, 8, cudaMemcpyDeviceToHost, st));
+        B2_CUDA(cudaStreamSynchronize(st));
+        *clips = size_t(c);
+      }
     }
   }
   if (!dev_ptrs) {

@@ -1,8 +1,38 @@
 // fft_stage.cuh -- fused shared-memory overlap-save FFT stage (+ rational polyphase).
-// (stub: filled in by the next milestone; the generic kernels cover every plan.)
+//
+// One CTA computes one block of one PAIR of signals (signal 2q in the real part,
+// 2q+1 in the imaginary part of a complex stream: the filters are real, so the
+// two never mix mathematically).  It replaces, in one launch,
+//
+//   K1  deinterleave + convert-in             data-io.c:13-57
+//   K2  dft_stage_fn  (overlap-save FIR, L/M)  cr.c:68-174      (PFFFT: pffft.c)
+//   K3  vpoly0        (rational polyphase)     poly-fir0.h:24-44
+//   K7  interleave + convert-out (float)       data-io.c:161-170
+//
+// so the L-times oversampled intermediate never leaves shared memory.
+//
+// Maths (plan.h closed form  out[j] = sum_k g[C + M j - L k] in[k]):
+// with k = k0 + M i + s and j = j0 + L i' + r the stage is L*M ordinary
+// convolutions at the base rate,
+//     out_r[i'] = sum_s sum_m g_rs[m] in_s[i' - m],   g_rs[m] = g[D + M r - L s + L M m],
+// D = C + M j0 - L k0, evaluated per block as circular convolutions of length n:
+// M forward FFTs, L*M spectrum products, L inverse FFTs.  The block grid is the
+// reference's own (k0 = -preload + b M V, V = n - span valid outputs per phase),
+// so whenever the reference emits a block's outputs the block's input is
+// complete and results do not depend on how the stream was chunked.
+//
+// FFT: n = R1*16*16 points, T = n/16 threads, 16 points per thread, three
+// register-radix passes (R1,16,16) with two shared-memory exchanges; the forward
+// transform is DIT and the inverse the mirrored DIF, so the spectrum stays in
+// registers between them.  Replaces PFFFT's radix-2/4 passes.
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+#include "fft_regs.cuh"
 #include "plan.h"
 #include "runtime.h"
 
@@ -11,19 +41,373 @@ namespace b2 {
 struct FftStageInfo {
   int stage_index = -1;
   bool fused_poly = false;
+  int log2n = 0, n = 0, L = 1, M = 1;
+  long k0 = 0;                   // input index of point 0 (phase 0) of block 0
+  int span = 0, v_base = 0;      // valid outputs per block and phase = n - span
+  int delta = 0;                 // halo (base-rate samples) kept in front of a block for the poly stage
+  int pL = 1, pM = 1, p_at0 = 0, p_pre = 0, nc = 0, ncp = 0;
+  size_t smem_bytes = 0;
+  int threads = 0;
+  int max_ctas_per_sm = 1;
 };
 
-struct RangeLH { long lo, hi; };
+struct FftKParams {
+  SigDesc in, out;
+  unsigned n_sig, n_pairs;
+  long b_first;
+  int n_blocks;
+  long o0, o1;
+  long k0;
+  int v_base, delta, us;         // us: stride of one output phase inside U
+  const void *spec, *tw2, *tw3, *edge, *ptab;
+  int pL, pM, p_at0, p_pre, nc, ncp;
+  unsigned ptab_bytes;
+};
 
-inline const char *fft_stage_prepare(DevicePlan *) { return nullptr; }
+#ifdef __CUDACC__
+
+template <typename R> __device__ __forceinline__ R ld_as(const void *p, int dtype, long long idx) {
+  switch (dtype) {
+    case 0: return R(static_cast<const float *>(p)[idx]);
+    case 1: return R(static_cast<const double *>(p)[idx]);
+    case 2: return R(static_cast<const int *>(p)[idx]);
+    default: return R(static_cast<const short *>(p)[idx]);
+  }
+}
+template <typename R> __device__ __forceinline__ void st_as(void *p, int dtype, long long idx, R v) {
+  if (dtype == 0) static_cast<float *>(p)[idx] = float(v);
+  else static_cast<double *>(p)[idx] = double(v);
+}
+
+template <int BYTES> __device__ __forceinline__ int phys(int p);
+template <> __device__ __forceinline__ int phys<8>(int p) { return p + (p >> 4) + (p >> 8); }
+template <> __device__ __forceinline__ int phys<16>(int p) { return p + (p >> 4) + (p >> 7); }
+
+__host__ __device__ inline long long ceil_div_ll(long long a, long long b) {   // b > 0
+  return a >= 0 ? (a + b - 1) / b : -((-a) / b);
+}
+
+// Per-item view of one signal pair.
+template <typename R>
+struct PairIn {
+  const void *p;
+  int dtype;
+  long long off0, off1, fs;
+  long vlo, vhi;
+  bool has1, vec;
+  typedef typename V2<R>::type C;
+  __device__ __forceinline__ C load(long k) const {
+    C c;
+    c.x = R(0);
+    c.y = R(0);
+    if (k >= vlo && k < vhi) {
+      if (vec) {
+        const float2 t = *reinterpret_cast<const float2 *>(static_cast<const float *>(p) + off0 + k * fs);
+        c.x = R(t.x);
+        c.y = R(t.y);
+      } else {
+        c.x = ld_as<R>(p, dtype, off0 + k * fs);
+        if (has1) c.y = ld_as<R>(p, dtype, off1 + k * fs);
+      }
+    }
+    return c;
+  }
+};
 
 template <typename R>
-inline R fft_stage_input_range(const FftStageInfo &, const Stage &, R r) { return r; }
-
-template <typename T>
-inline const char *fft_stage_run(const DevicePlan &, const FftStageInfo &, const T *, size_t, long, long, long,
-                                 T *, size_t, long, long, long, unsigned, cudaStream_t) {
-  return "internal: fused FFT stage not built";
+__device__ __forceinline__ PairIn<R> make_pair_in(const SigDesc &d, unsigned pair, unsigned n_sig) {
+  PairIn<R> pi;
+  const unsigned s0 = 2 * pair, s1 = s0 + 1;
+  pi.p = d.p;
+  pi.dtype = d.dtype;
+  pi.fs = d.frame_stride;
+  pi.off0 = (long long)(s0 / d.channels) * d.clip_stride + (long long)(s0 % d.channels) * d.chan_stride - d.base * d.frame_stride;
+  pi.has1 = s1 < n_sig;
+  pi.off1 = pi.has1 ? (long long)(s1 / d.channels) * d.clip_stride + (long long)(s1 % d.channels) * d.chan_stride - d.base * d.frame_stride
+                    : pi.off0;
+  pi.vlo = d.vlo;
+  pi.vhi = d.vhi;
+  pi.vec = d.dtype == 0 && pi.has1 && pi.off1 == pi.off0 + 1 && !(pi.off0 & 1) && !(pi.fs & 1) &&
+           !(reinterpret_cast<unsigned long long>(d.p) & 7);
+  return pi;
 }
+
+template <typename R>
+__device__ __forceinline__ void store_pair(const SigDesc &d, long long off0, long long off1, bool has1, bool vec, long k,
+                                           typename V2<R>::type v) {
+  if (vec) {
+    *reinterpret_cast<float2 *>(static_cast<float *>(d.p) + off0 + k * d.frame_stride) = make_float2(float(v.x), float(v.y));
+  } else {
+    st_as<R>(d.p, d.dtype, off0 + k * d.frame_stride, v.x);
+    if (has1) st_as<R>(d.p, d.dtype, off1 + k * d.frame_stride, v.y);
+  }
+}
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+      "r"(phase)
+      : "memory");
+}
+// TMA bulk copy global -> shared (1-D), completion signalled on the mbarrier.
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(dst_smem)),
+               "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// The kernel.  R: engine real type.  n = 2^LOG2N.  L, M: stage ratio.  POLY: a
+// rational polyphase stage (vpoly0) consumes the block from shared memory.
+// ---------------------------------------------------------------------------
+template <typename R, int LOG2N, int L, int M, bool POLY>
+__global__ void __launch_bounds__((1 << LOG2N) / 16) k_fft_stage(const FftKParams P) {
+  typedef typename V2<R>::type C;
+  constexpr int N = 1 << LOG2N, R1 = N / 256, T = N / 16, NB1 = 16 / R1;
+  constexpr int EB = int(sizeof(C));
+  constexpr int BUF_ELEMS = N + (N >> 4) + (EB == 8 ? (N >> 8) : (N >> 7)) + 8;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C *buf = reinterpret_cast<C *>(smem_raw);
+  C *U = buf + BUF_ELEMS;
+  R *tab = reinterpret_cast<R *>(U + size_t(L) * P.us);
+  __shared__ __align__(8) unsigned long long tab_bar;
+
+  const int t = threadIdx.x;
+  const C *__restrict__ tw2 = static_cast<const C *>(P.tw2);
+  const C *__restrict__ tw3 = static_cast<const C *>(P.tw3);
+  const C *__restrict__ spec = static_cast<const C *>(P.spec);
+
+  if (POLY) {   // K8's table: staged once per CTA with a TMA bulk copy, waited for before the first use
+    if (t == 0) {
+      mbar_init(&tab_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (t == 0) {
+      mbar_expect_tx(&tab_bar, P.ptab_bytes);
+      tma_bulk_g2s(tab, P.ptab, P.ptab_bytes, &tab_bar);
+    }
+  }
+  bool tab_ready = !POLY;
+
+  const int j2 = t % R1, G2 = t / R1, e0 = G2 * T + j2;
+  const long LV = long(L) * P.v_base;
+  const long long n_items = (long long)P.n_pairs * P.n_blocks;
+
+  for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const unsigned pair = unsigned(item / P.n_blocks);
+    const long b = P.b_first + long(item % P.n_blocks);
+    const PairIn<R> pin = make_pair_in<R>(P.in, pair, P.n_sig);
+    const long k0 = P.k0 + b * long(M) * P.v_base;   // input index of point 0, phase 0
+
+    // ---- halo correction terms (threads < L*delta), see file header -------------
+    C corr;
+    corr.x = R(0);
+    corr.y = R(0);
+    if (POLY && b > 0 && t < L * P.delta) {
+      const int r = t / P.delta, ii = t % P.delta - P.delta;   // i' in [-delta, 0)
+      const R *__restrict__ edge = static_cast<const R *>(P.edge);
+      for (int s = 0; s < M; ++s)
+        for (int e = 0; e < -ii; ++e) {       // m = -e, i' - m = ii + e < 0
+          const R gv = edge[(r * M + s) * P.delta + e];
+          const C a = pin.load(k0 + long(M) * (ii + e) + s);
+          const C w = pin.load(k0 + long(M) * (N + ii + e) + s);
+          corr.x += gv * (a.x - w.x);
+          corr.y += gv * (a.y - w.y);
+        }
+    }
+
+    // ---- forward transforms: Z[s][q] = spectrum bin t + T q of input phase s -----
+    C Z[M][16];
+#pragma unroll
+    for (int s = 0; s < M; ++s) {
+      C v[16];
+#pragma unroll
+      for (int u = 0; u < NB1; ++u)
+#pragma unroll
+        for (int m1 = 0; m1 < R1; ++m1) v[u * R1 + m1] = pin.load(k0 + long(M) * (t + T * u + 256 * m1) + s);
+      __syncthreads();   // buf (and U) free: previous item / phase finished reading
+#pragma unroll
+      for (int u = 0; u < NB1; ++u) {
+        C a[R1];
+#pragma unroll
+        for (int m1 = 0; m1 < R1; ++m1) a[m1] = v[u * R1 + m1];
+        Dft<R1>::template run<false>(a);
+        const int g = t + T * u, base = R1 * (g >> 4) + T * (g & 15);
+#pragma unroll
+        for (int q1 = 0; q1 < R1; ++q1) buf[phys<EB>(base + q1)] = a[q1];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int m = 0; m < 16; ++m) v[m] = buf[phys<EB>(e0 + R1 * m)];
+#pragma unroll
+      for (int m = 1; m < 16; ++m) v[m] = cmul(v[m], tw2[m * R1 + j2]);
+      Dft<16>::template run<false>(v);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) buf[phys<EB>(e0 + R1 * q)] = v[q];
+      __syncthreads();
+#pragma unroll
+      for (int m = 0; m < 16; ++m) v[m] = buf[phys<EB>(t + T * m)];
+#pragma unroll
+      for (int m = 1; m < 16; ++m) v[m] = cmul(v[m], tw3[m * T + t]);
+      Dft<16>::template run<false>(v);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) Z[s][q] = v[q];
+    }
+
+    // ---- per output phase: spectrum product, inverse transform into U ------------
+#pragma unroll
+    for (int r = 0; r < L; ++r) {
+      C v[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        C acc = cmul(Z[0][q], spec[((r * M + 0) * 16 + q) * T + t]);
+#pragma unroll
+        for (int s = 1; s < M; ++s) {
+          const C e = cmul(Z[s][q], spec[((r * M + s) * 16 + q) * T + t]);
+          acc.x += e.x;
+          acc.y += e.y;
+        }
+        v[q] = acc;
+      }
+      Dft<16>::template run<true>(v);
+#pragma unroll
+      for (int m = 1; m < 16; ++m) v[m] = cmulc(v[m], tw3[m * T + t]);
+      __syncthreads();   // previous readers of buf are done
+#pragma unroll
+      for (int m = 0; m < 16; ++m) buf[phys<EB>(t + T * m)] = v[m];
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 16; ++q) v[q] = buf[phys<EB>(e0 + R1 * q)];
+      Dft<16>::template run<true>(v);
+#pragma unroll
+      for (int m = 1; m < 16; ++m) v[m] = cmulc(v[m], tw2[m * R1 + j2]);
+#pragma unroll
+      for (int m = 0; m < 16; ++m) buf[phys<EB>(e0 + R1 * m)] = v[m];
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < NB1; ++u) {
+        C a[R1];
+        const int g = t + T * u, base = R1 * (g >> 4) + T * (g & 15);
+#pragma unroll
+        for (int q1 = 0; q1 < R1; ++q1) a[q1] = buf[phys<EB>(base + q1)];
+        Dft<R1>::template run<true>(a);
+#pragma unroll
+        for (int m1 = 0; m1 < R1; ++m1) {
+          const int i = g + 256 * m1;            // block-local output index i'
+          if (i < P.v_base) U[r * P.us + P.delta + i] = a[m1];
+          else if (POLY && i >= N - P.delta) U[r * P.us + i - (N - P.delta)] = a[m1];   // circular tail = halo (uncorrected)
+        }
+      }
+    }
+    __syncthreads();
+
+    const long J0 = b * LV;   // first valid output of this block (output-rate index of the FFT stage)
+    if (POLY) {
+      // halo: add the wrap-around correction; the intermediate does not exist before index 0 (cr.c:487-490)
+      if (t < L * P.delta) {
+        const int r = t / P.delta, hi = t % P.delta;
+        C h = U[r * P.us + hi];
+        h.x += corr.x;
+        h.y += corr.y;
+        if (b == 0) { h.x = R(0); h.y = R(0); }
+        U[r * P.us + hi] = h;
+      }
+      if (!tab_ready) {
+        mbar_wait(&tab_bar, 0);
+        tab_ready = true;
+      }
+      __syncthreads();
+
+      // ---- K3: rational polyphase stage out of shared memory ----------------------
+      const long long Q0 = (long long)J0 - P.nc + 1 + P.p_pre, Q1 = Q0 + LV;
+      long n_lo = b == 0 ? 0 : long(max(0LL, ceil_div_ll(Q0 * P.pL - P.p_at0, P.pM)));
+      long n_hi = long(max(0LL, ceil_div_ll(Q1 * P.pL - P.p_at0, P.pM)));
+      n_lo = max(n_lo, P.o0);
+      n_hi = min(n_hi, P.o1);
+      const unsigned s0 = 2 * pair, s1 = s0 + 1;
+      const bool has1 = s1 < P.n_sig;
+      const long long ooff0 = (long long)(s0 / P.out.channels) * P.out.clip_stride +
+                              (long long)(s0 % P.out.channels) * P.out.chan_stride - P.out.base * P.out.frame_stride;
+      const long long ooff1 = has1 ? (long long)(s1 / P.out.channels) * P.out.clip_stride +
+                                         (long long)(s1 % P.out.channels) * P.out.chan_stride - P.out.base * P.out.frame_stride
+                                   : ooff0;
+      const bool ovec = P.out.dtype == 0 && has1 && ooff1 == ooff0 + 1 && !(ooff0 & 1) && !(P.out.frame_stride & 1) &&
+                        !(reinterpret_cast<unsigned long long>(P.out.p) & 7);
+      const long ubase = J0 - long(L) * P.delta;   // output-rate index of U's first element
+      if (n_lo + t < n_hi) {
+        const long long at = (long long)P.p_at0 + (long long)(n_lo + t) * P.pM;
+        long div = long(at / P.pL);
+        int rem = int(at % P.pL);
+        const int dstep = int((long long)T * P.pM / P.pL), rstep = int((long long)T * P.pM % P.pL);
+        for (long nn = n_lo + t; nn < n_hi; nn += T) {
+          const int rel = int(div - P.p_pre - ubase);
+          const R *__restrict__ c = tab + rem * P.ncp;
+          R ax = R(0), ay = R(0);
+          for (int k = 0; k < P.nc; ++k) {
+            const int idx = rel + k;
+            const C u = U[(idx % L) * P.us + idx / L];
+            const R cv = c[k];
+            ax = fma(cv, u.x, ax);
+            ay = fma(cv, u.y, ay);
+          }
+          C o;
+          o.x = ax;
+          o.y = ay;
+          store_pair<R>(P.out, ooff0, ooff1, has1, ovec, nn, o);
+          div += dstep;
+          rem += rstep;
+          if (rem >= P.pL) { rem -= P.pL; ++div; }
+        }
+      }
+    } else {
+      // ---- emit the block: out[J0 + L i' + r], interleaving the L output phases ----
+      const unsigned s0 = 2 * pair, s1 = s0 + 1;
+      const bool has1 = s1 < P.n_sig;
+      const long long ooff0 = (long long)(s0 / P.out.channels) * P.out.clip_stride +
+                              (long long)(s0 % P.out.channels) * P.out.chan_stride - P.out.base * P.out.frame_stride;
+      const long long ooff1 = has1 ? (long long)(s1 / P.out.channels) * P.out.clip_stride +
+                                         (long long)(s1 % P.out.channels) * P.out.chan_stride - P.out.base * P.out.frame_stride
+                                   : ooff0;
+      const bool ovec = P.out.dtype == 0 && has1 && ooff1 == ooff0 + 1 && !(ooff0 & 1) && !(P.out.frame_stride & 1) &&
+                        !(reinterpret_cast<unsigned long long>(P.out.p) & 7);
+      const long lo = max(J0, P.o0), hi = min(J0 + LV, P.o1);
+      for (long j = lo + t; j < hi; j += T) {
+        const int idx = int(j - J0);
+        store_pair<R>(P.out, ooff0, ooff1, has1, ovec, j, U[(idx % L) * P.us + idx / L]);
+      }
+    }
+  }
+  if (POLY && !tab_ready) mbar_wait(&tab_bar, 0);   // never exit with a bulk copy in flight
+}
+
+#endif  // __CUDACC__
+
+// ---- host side ---------------------------------------------------------------
+const char *fft_stage_prepare(DevicePlan *dp);
+
+struct RangeLH { long lo, hi; };
+// Input range (of the stage feeding the fused launch) needed for final outputs [lo, hi) of the launch.
+RangeLH fft_stage_input_range(const FftStageInfo &fi, long lo, long hi);
+
+const char *fft_stage_run(const DevicePlan &dp, const FftStageInfo &fi, const SigDesc &in, const SigDesc &out,
+                          long o0, long o1, unsigned n_sig, cudaStream_t st);
 
 }  // namespace b2

@@ -482,7 +482,7 @@ void CallEmu::run_stage(int i) {
           }
         } else {
           const int m = st.fd_shift;
-          next_occ += (N >> m) - ((((1 << m) - 1) * N + overlap) >> m);
+          next_occ += N - ((((1 << m) - 1) * N + overlap) >> m);   // reserve N, trim (cr.c:84,169)
         }
       }
       e.input_size = (N - e.at + L - 1) / L;

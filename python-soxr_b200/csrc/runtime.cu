@@ -47,7 +47,7 @@ void PinnedBuf::release() {
 }
 
 DevicePlan::~DevicePlan() {
-  for (DevStage &s : stages) { s.g.release(); s.table.release(); s.spec.release(); s.twid.release(); s.ptab.release(); }
+  for (DevStage &s : stages) { s.g.release(); s.table.release(); s.spec.release(); s.twid.release(); s.edge.release(); s.ptab.release(); }
 }
 
 Workspace::~Workspace() {
@@ -75,7 +75,7 @@ struct PlanKey {
   double precision, passband_end, stopband_begin;
   unsigned long qflags, rflags;
   unsigned min_dft, large_dft, coef_kb;
-  int device;
+  int device, arith_double;
   bool operator<(const PlanKey &o) const { return std::memcmp(this, &o, sizeof *this) < 0; }
 };
 std::mutex g_plan_mu;
@@ -101,7 +101,7 @@ void release_workspace(Workspace *w) {
 }
 
 const char *get_device_plan(double io_ratio, const QSpec &q, const RSpec &r, double multiplier,
-                            std::shared_ptr<DevicePlan> *out) {
+                            bool arith_double, std::shared_ptr<DevicePlan> *out) {
   PlanKey key;
   std::memset(&key, 0, sizeof key);
   std::memcpy(&key.ratio_bits, &io_ratio, 8);
@@ -117,12 +117,13 @@ const char *get_device_plan(double io_ratio, const QSpec &q, const RSpec &r, dou
   int dev = 0;
   B2_CUDA(cudaGetDevice(&dev));
   key.device = dev;
+  key.arith_double = arith_double ? 1 : 0;
   std::lock_guard<std::mutex> l(g_plan_mu);
   auto it = g_plans.find(key);
   if (it != g_plans.end()) { *out = it->second; return nullptr; }
   auto dp = std::make_shared<DevicePlan>();
   if (const char *e = make_plan(io_ratio, q, r, multiplier, &dp->plan)) return e;
-  dp->is_double = dp->plan.is_double;
+  dp->is_double = arith_double;
   dp->stages.resize(dp->plan.stages.size());
   for (size_t i = 0; i < dp->plan.stages.size(); ++i) {
     const Stage &s = dp->plan.stages[i];
@@ -272,15 +273,51 @@ namespace {
 
 struct Range { long lo, hi; };
 
-// Output range of stage s-1 needed to produce outputs [r.lo, r.hi) of stage s.
-Range input_range(const DevicePlan &dp, size_t s, Range r) {
-  const Stage &st = dp.plan.stages[s];
+// Output range of stage s-1 needed to produce outputs [r.lo, r.hi) of stage `last`,
+// where stages [s, last] run as one launch.
+Range input_range(const DevicePlan &dp, size_t s, size_t last, Range r) {
   if (r.hi <= r.lo) return {0, 0};
-  Range need{stage_input_first(st, r.lo), stage_input_needed(st, r.hi)};
-  if (dp.fft && dp.fft->stage_index == int(s)) need = fft_stage_input_range(*dp.fft, st, r);
+  Range need;
+  if (dp.fft && dp.fft->stage_index == int(s)) {
+    const RangeLH t = fft_stage_input_range(*dp.fft, r.lo, r.hi);
+    need = {t.lo, t.hi};
+  } else {
+    const Stage &st = dp.plan.stages[s];
+    need = {stage_input_first(st, r.lo), stage_input_needed(st, r.hi)};
+  }
+  (void)last;
   need.lo = std::max(need.lo, 0L);
   need.hi = std::max(need.hi, need.lo);
   return need;
+}
+
+// element-wise copy between two descriptors (K1 / float K7 when no fused launch touches the user buffers)
+template <typename T>
+__global__ void k_sig_copy(SigDesc in, SigDesc out, long o0, long n, unsigned n_sig) {
+  const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long k = o0 + i;
+  for (unsigned s = blockIdx.y; s < n_sig; s += gridDim.y) {
+    T v = T(0);
+    if (k >= in.vlo && k < in.vhi)
+      v = ld_as<T>(in.p, in.dtype, (long long)(s / in.channels) * in.clip_stride + (long long)(s % in.channels) * in.chan_stride +
+                                       (long long)(k - in.base) * in.frame_stride);
+    st_as<T>(out.p, out.dtype, (long long)(s / out.channels) * out.clip_stride + (long long)(s % out.channels) * out.chan_stride +
+                                   (long long)(k - out.base) * out.frame_stride, v);
+  }
+}
+
+template <typename T>
+const char *sig_copy(const SigDesc &in, const SigDesc &out, long o0, long o1, unsigned n_sig, cudaStream_t st) {
+  if (o1 <= o0 || !n_sig) return nullptr;
+  k_sig_copy<T><<<grid_for(size_t(o1 - o0), n_sig), 256, 0, st>>>(in, out, o0, o1 - o0, n_sig);
+  B2_COUNT_LAUNCH();
+  B2_CUDA(cudaGetLastError());
+  return nullptr;
+}
+
+template <typename T> bool is_planar(const SigDesc &d) {
+  return d.dtype == (sizeof(T) == 8 ? 1 : 0) && d.frame_stride == 1 && d.channels == 1;
 }
 
 template <typename T>
@@ -309,66 +346,89 @@ const char *run_stage_generic(const DevicePlan &dp, size_t si, SigIn<T> in, SigO
 }
 
 template <typename T>
-const char *run_range_t(const DevicePlan &dp, const XView &x, unsigned n_sig, long o0, long o1, T *Y,
-                        size_t y_stride, Workspace *ws, cudaStream_t st) {
+const char *run_range_t(const DevicePlan &dp, const SigDesc &in0, long n_in_total, unsigned n_sig, long o0, long o1,
+                        const SigDesc &out0, Workspace *ws, cudaStream_t st) {
   const size_t S = dp.plan.stages.size();
   if (o1 <= o0 || !n_sig) return nullptr;
-  const long x_vhi = x.n_in_total >= 0 ? std::min(x.hi, x.n_in_total) : x.hi;
-  if (S == 0) {   // unity ratio: samples pass through (cr.c:347; zero-extended by flush)
-    B2_CUDA(cudaMemsetAsync(Y, 0, size_t(n_sig) * y_stride * sizeof(T), st));
-    const long lo = std::max(o0, x.base), hi = std::min(o1, x_vhi);
-    if (hi > lo)
-      B2_CUDA(cudaMemcpy2DAsync(Y + (lo - o0), y_stride * sizeof(T),
-                                static_cast<const T *>(x.p) + (lo - x.base), x.stride * sizeof(T),
-                                size_t(hi - lo) * sizeof(T), n_sig, cudaMemcpyDeviceToDevice, st));
-    return nullptr;
-  }
-  // ranges back to front
-  std::vector<Range> out_r(S);
-  out_r[S - 1] = {o0, o1};
-  for (size_t s = S - 1; s > 0; --s) out_r[s - 1] = input_range(dp, s, out_r[s]);
-  const Range xin = input_range(dp, 0, out_r[0]);
-  if (xin.hi > xin.lo && xin.lo < x.base) return "internal: input history trimmed too far";
-  if (x.n_in_total < 0 && xin.hi > x.hi) return "internal: output range needs input that has not arrived";
+  SigDesc cur = in0;
+  if (n_in_total >= 0) cur.vhi = std::min(cur.vhi, n_in_total);
+  if (S == 0)   // unity ratio: samples pass through (cr.c:347; zero-extended by flush)
+    return sig_copy<T>(cur, out0, o0, o1, n_sig, st);
 
-  SigIn<T> in{static_cast<const T *>(x.p), x.stride, x.base, std::max(0L, x.base), x_vhi};
-  DevBuf *in_buf = nullptr;   // which scratch buffer `in` lives in (nullptr: the caller's X)
+  // launches: [first, last] stage index ranges, and the output range of each, back to front
+  struct Launch { size_t first, last; bool fft; Range r; };
+  std::vector<Launch> launches;
   for (size_t s = 0; s < S; ++s) {
     const bool use_fft = dp.fft && dp.fft->stage_index == int(s);
-    const size_t last = (use_fft && dp.fft->fused_poly) ? s + 1 : s;   // last stage covered by this launch
-    const Range r = out_r[last];
-    const size_t len = size_t(std::max(0L, r.hi - r.lo));
-    SigOut<T> out;
-    DevBuf *out_buf = nullptr;
-    if (last + 1 == S) out = SigOut<T>{Y, y_stride, o0};
-    else {
-      out_buf = (in_buf == &ws->t0) ? &ws->t1 : &ws->t0;
-      const size_t stride = (len + 63) & ~size_t(63);
-      if (const char *e = out_buf->reserve(std::max<size_t>(1, stride * n_sig) * sizeof(T))) return e;
-      out = SigOut<T>{out_buf->as<T>(), stride, r.lo};
-    }
-    const char *e = use_fft ? fft_stage_run<T>(dp, *dp.fft, in.p, in.stride, in.base, in.vlo, in.vhi, out.p,
-                                               out.stride, out.base, r.lo, r.hi, n_sig, st)
-                            : run_stage_generic<T>(dp, s, in, out, r, n_sig, st);
-    if (e) return e;
+    const size_t last = (use_fft && dp.fft->fused_poly) ? s + 1 : s;
+    launches.push_back({s, last, use_fft, {0, 0}});
     s = last;
-    // intermediate signals exist for index >= 0 only (FIFO preloads are zeros, cr.c:487-490)
-    in = SigIn<T>{out.p, out.stride, out.base, std::max(0L, r.lo), r.hi};
-    in_buf = out_buf;
+  }
+  launches.back().r = {o0, o1};
+  for (size_t i = launches.size() - 1; i > 0; --i)
+    launches[i - 1].r = input_range(dp, launches[i].first, launches[i].last, launches[i].r);
+  const Range xin = input_range(dp, launches[0].first, launches[0].last, launches[0].r);
+  if (xin.hi > xin.lo && xin.lo < in0.base) return "internal: input history trimmed too far";
+  if (n_in_total < 0 && xin.hi > in0.vhi) return "internal: output range needs input that has not arrived";
+
+  DevBuf *cur_buf = nullptr;   // which scratch buffer `cur` lives in
+  for (size_t i = 0; i < launches.size(); ++i) {
+    const Launch &ln = launches[i];
+    const bool is_last = i + 1 == launches.size();
+    const size_t len = size_t(std::max(0L, ln.r.hi - ln.r.lo));
+    // generic kernels read planar engine-precision input only (K1 as a separate pass)
+    if (!ln.fft && !is_planar<T>(cur)) {
+      const long lo = std::max(xin.lo, cur.vlo), hi = std::max(lo, std::min(xin.hi, cur.vhi));
+      const size_t stride = (size_t(hi - lo) + 63) & ~size_t(63);
+      if (const char *e = ws->x.reserve(std::max<size_t>(1, stride * n_sig) * sizeof(T))) return e;
+      const SigDesc px = planar_desc(ws->x.p, sizeof(T) == 8, stride, lo, lo, hi);
+      if (const char *e = sig_copy<T>(cur, px, lo, hi, n_sig, st)) return e;
+      cur = px;
+    }
+    SigDesc dst;
+    DevBuf *dst_buf = nullptr;
+    const bool direct = is_last && (ln.fft || is_planar<T>(out0));
+    if (direct) dst = out0;
+    else {
+      dst_buf = (cur_buf == &ws->t0) ? &ws->t1 : &ws->t0;
+      const size_t stride = (len + 63) & ~size_t(63);
+      if (const char *e = dst_buf->reserve(std::max<size_t>(1, stride * n_sig) * sizeof(T))) return e;
+      // intermediate signals exist for index >= 0 only (FIFO preloads are zeros, cr.c:487-490)
+      dst = planar_desc(dst_buf->p, sizeof(T) == 8, stride, ln.r.lo, std::max(0L, ln.r.lo), ln.r.hi);
+    }
+    const char *e;
+    if (ln.fft) e = fft_stage_run(dp, *dp.fft, cur, dst, ln.r.lo, ln.r.hi, n_sig, st);
+    else {
+      SigIn<T> gi{static_cast<const T *>(cur.p), size_t(cur.clip_stride), cur.base, cur.vlo, cur.vhi};
+      SigOut<T> go{static_cast<T *>(dst.p), size_t(dst.clip_stride), dst.base};
+      e = run_stage_generic<T>(dp, ln.first, gi, go, ln.r, n_sig, st);
+    }
+    if (e) return e;
+    if (is_last && !direct) return sig_copy<T>(dst, out0, o0, o1, n_sig, st);
+    cur = dst;
+    cur_buf = dst_buf;
   }
   return nullptr;
 }
 }  // namespace
 
-const char *run_range(const DevicePlan &dp, const XView &x, unsigned n_sig, long o0, long o1, void *Y,
-                      size_t y_stride, Workspace *ws, cudaStream_t stream) {
-  return dp.is_double ? run_range_t<double>(dp, x, n_sig, o0, o1, static_cast<double *>(Y), y_stride, ws, stream)
-                      : run_range_t<float>(dp, x, n_sig, o0, o1, static_cast<float *>(Y), y_stride, ws, stream);
+const char *run_range(const DevicePlan &dp, const SigDesc &in, long n_in_total, unsigned n_sig, long o0, long o1,
+                      const SigDesc &out, Workspace *ws, cudaStream_t stream) {
+  return dp.is_double ? run_range_t<double>(dp, in, n_in_total, n_sig, o0, o1, out, ws, stream)
+                      : run_range_t<float>(dp, in, n_in_total, n_sig, o0, o1, out, ws, stream);
 }
 
 long history_needed_from(const DevicePlan &dp, long o) {
   Range r{o, o + 1};
-  for (size_t s = dp.plan.stages.size(); s-- > 0;) r = input_range(dp, s, r);
+  std::vector<std::pair<size_t, size_t>> launches;
+  const size_t S = dp.plan.stages.size();
+  for (size_t s = 0; s < S; ++s) {
+    const bool use_fft = dp.fft && dp.fft->stage_index == int(s);
+    const size_t last = (use_fft && dp.fft->fused_poly) ? s + 1 : s;
+    launches.push_back({s, last});
+    s = last;
+  }
+  for (size_t i = launches.size(); i-- > 0;) r = input_range(dp, launches[i].first, launches[i].second, r);
   return r.lo;
 }
 

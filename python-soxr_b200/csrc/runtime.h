@@ -44,6 +44,7 @@ struct DevStage {
   // fused FFT stage data (fft_stage.cuh)
   DevBuf spec;    // filter spectra in kernel order
   DevBuf twid;    // twiddles
+  DevBuf edge;    // first taps of each polyphase component (halo correction)
   DevBuf ptab;    // rational poly table [phase][tap] for the fused kernel
 };
 
@@ -51,15 +52,17 @@ struct FftStageInfo;   // fft_stage.cuh
 
 struct DevicePlan {
   Plan plan;
-  bool is_double = false;
+  bool is_double = false;   // ARITHMETIC type of the device path (plan.is_double is the reference's engine)
   std::vector<DevStage> stages;
   std::shared_ptr<FftStageInfo> fft;   // non-null if the fused FFT kernel applies
   ~DevicePlan();
 };
 
 // Immutable plan cache (keyed by ratio bits, preset, flags, gain, device).
+// arith_double: run the device arithmetic in f64 (else f32).  The filter design always follows
+// the reference's engine choice (soxr.c:447), only the sample arithmetic type differs.
 const char *get_device_plan(double io_ratio, const QSpec &q, const RSpec &r, double multiplier,
-                            std::shared_ptr<DevicePlan> *out);
+                            bool arith_double, std::shared_ptr<DevicePlan> *out);
 
 // Per-call scratch: reused across calls through a pool so concurrent callers
 // (the reference's thread-pool tests) never share buffers.
@@ -80,19 +83,30 @@ struct IoLayout {
 };
 inline size_t dtype_size(int dt) { return dt == 0 ? 4 : dt == 1 ? 8 : dt == 2 ? 4 : 2; }
 
-// Planar engine-precision view of the input history.
-struct XView {
-  void *p;            // T*
-  size_t stride;      // elements per signal
-  long base;          // logical index of element 0
-  long hi;            // exclusive logical end of valid data
-  long n_in_total;    // known total length (flush seen) or -1
+// Signals in user layout or planar scratch:
+//   element(s, k) = p[(s / channels) * clip_stride + (s % channels) * chan_stride + (k - base) * frame_stride]
+struct SigDesc {
+  void *p = nullptr;
+  int dtype = 0;                 // B200SOXR_FLOAT32.. (0 f32, 1 f64, 2 i32, 3 i16)
+  unsigned channels = 1;
+  long long clip_stride = 0, frame_stride = 1, chan_stride = 0;
+  long base = 0;                 // logical index of element 0
+  long vlo = 0, vhi = 0;         // reads outside [vlo, vhi) are zero (inputs only)
 };
+// planar scratch of engine-precision samples: signal s at p[s*stride + (k - base)]
+inline SigDesc planar_desc(void *p, bool is_double, size_t stride, long base, long vlo, long vhi) {
+  SigDesc d;
+  d.p = p; d.dtype = is_double ? 1 : 0; d.channels = 1; d.clip_stride = (long long)stride;
+  d.frame_stride = 1; d.chan_stride = 0; d.base = base; d.vlo = vlo; d.vhi = vhi;
+  return d;
+}
 
-// Compute final outputs [o0, o1) of every signal into planar Y (stride y_stride,
-// element 0 == output o0).  Generic path; the fused path is selected inside.
-const char *run_range(const DevicePlan &dp, const XView &x, unsigned n_sig, long o0, long o1, void *Y,
-                      size_t y_stride, Workspace *ws, cudaStream_t stream);
+// Compute final outputs [o0, o1) of every signal.  `in` holds input samples for
+// logical indices [in.vlo, in.vhi) (zero outside; n_in_total < 0 means more input
+// may still arrive, so reading beyond in.vhi is an error).  `out` is a float32 /
+// float64 destination in any layout (element 0 of a signal == output out.base).
+const char *run_range(const DevicePlan &dp, const SigDesc &in, long n_in_total, unsigned n_sig, long o0, long o1,
+                      const SigDesc &out, Workspace *ws, cudaStream_t stream);
 
 // Lowest input index any output >= o can still depend on (for history trimming).
 long history_needed_from(const DevicePlan &dp, long o);

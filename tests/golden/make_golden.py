@@ -64,6 +64,16 @@ STREAM_CASES = {
     'cfg3_stream_1024': (2, 20000, 8, 'float32', 44100, 16000, 'HQ', 1024),
     'vhq_480':          (21, 12000, 2, 'float32', 48000, 44100, 'VHQ', 480),
     'up_17':            (22, 3000, 1, 'float64', 32000, 44100, 'HQ', 17),
+    # one per remaining plan shape: F-domain /2, half-band chain, irrational (vpoly2/3), x6 post stage, LQ, QQ
+    'fdec_i16_1000':    (23, 20000, 1, 'int16', 96000, 48000, 'HQ', 1000),
+    'half_777':         (24, 30000, 2, 'float32', 48000, 8000, 'HQ', 777),
+    'irr_vhq_509':      (25, 9000, 1, 'float64', 44100, 47999.5, 'VHQ', 509),
+    'irr_hq_1024':      (26, 9000, 1, 'float32', 47999, 44100, 'HQ', 1024),
+    'up6_101':          (27, 5000, 1, 'float32', 8000, 48000, 'HQ', 101),
+    'lq_480':           (28, 9000, 2, 'float32', 48000, 44100, 'LQ', 480),
+    'qq_300':           (29, 6000, 1, 'float32', 44100, 22050, 'QQ', 300),
+    'vhq_dn3_2000':     (30, 30000, 1, 'float32', 48000, 16000, 'VHQ', 2000),
+    'hq_up_4096':       (31, 30000, 2, 'float32', 44100, 48000, 'HQ', 4096),
 }
 
 
