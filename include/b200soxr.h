@@ -133,8 +133,10 @@ B200SOXR_API b200soxr_error_t b200soxr_oneshot(double input_rate, double output_
  *             B200SOXR_BATCH_DOUBLE       force the f64 engine (SOXR_DOUBLE_PRECISION)
  *             B200SOXR_BATCH_EMULATE_CALLS int16 dither: replay the div_len call
  *                                          partition of csoxr_divide_proc (soxr_ext.cpp:239-257)
- *      `cuda_stream` is a cudaStream_t (NULL => default per-library stream; host
- *      pointers => synchronous on return; device pointers => asynchronous).      */
+ *      `cuda_stream` is a cudaStream_t.  Host pointers: NULL => a private stream of the
+ *      library; the call is synchronous (copies included).  Device pointers: the work
+ *      is enqueued on `cuda_stream` as given (NULL => CUDA's legacy default stream) and
+ *      the call returns without waiting.                                          */
 #define B200SOXR_BATCH_DEVICE_PTRS   1u
 #define B200SOXR_BATCH_NO_DITHER     2u
 #define B200SOXR_BATCH_DOUBLE        4u

@@ -18,6 +18,7 @@
 
 #include "../../include/b200soxr.h"
 #include "plan.h"
+#include "fft_stage.cuh"
 #include "runtime.h"
 
 using namespace b2;
@@ -369,7 +370,7 @@ b200soxr_error_t b200soxr_process(b200soxr_t p, void const *in, size_t ilen0, si
         SigDesc od;
         od.p = dev_out; od.dtype = ot; od.channels = ch; od.clip_stride = 0;
         od.frame_stride = lay.frame_stride; od.chan_stride = lay.chan_stride; od.base = p->out_done;
-        if ((e = run_range(*p->dp, xin, p->n_in_total, ch, p->out_done, p->out_done + long(odone), od, ws, st)))
+        if ((e = run_range(*p->dp, xin, p->n_in_total, ch, ch, p->out_done, p->out_done + long(odone), od, ws, st)))
           return p->error = e;
       }
     } else {
@@ -377,7 +378,7 @@ b200soxr_error_t b200soxr_process(b200soxr_t p, void const *in, size_t ilen0, si
       if ((e = ws->y.reserve(ys * ch * es))) return p->error = e;
       if (odone) {
         const SigDesc yd = planar_desc(ws->y.p, p->dp->is_double, ys, p->out_done, 0, 0);
-        if ((e = run_range(*p->dp, xin, p->n_in_total, ch, p->out_done, p->out_done + long(odone), yd, ws, st)))
+        if ((e = run_range(*p->dp, xin, p->n_in_total, ch, ch, p->out_done, p->out_done + long(odone), yd, ws, st)))
           return p->error = e;
       }
       DitherCfg dc;
@@ -444,6 +445,14 @@ b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *d, void co
   if (d->dtype < 0 || d->dtype > 3) return "invalid io datatype(s)";
   if (!d->channels || !d->n_clips) return "invalid # of channels";
   if (!device_ok()) return kNoDevice;
+  if ((d->flags & B200SOXR_BATCH_DEVICE_PTRS) && in) {
+    // run on the device that owns the buffers (one process may drive several GPUs)
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, in) == cudaSuccess && pa.type == cudaMemoryTypeDevice) {
+      int cur = -1;
+      if (cudaGetDevice(&cur) == cudaSuccess && cur != pa.device) B2_CUDA(cudaSetDevice(pa.device));
+    } else cudaGetLastError();
+  }
   const double io_ratio = d->in_rate / d->out_rate;
   const QSpec q = quality_spec(d->quality, (d->flags & B200SOXR_BATCH_DOUBLE) ? B200SOXR_DOUBLE_PRECISION : 0);
   std::shared_ptr<DevicePlan> dp;
@@ -458,7 +467,10 @@ b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *d, void co
 
   Workspace *ws = acquire_workspace();
   struct Rel { Workspace *w; ~Rel() { release_workspace(w); } } rel{ws};
-  cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ws->stream;
+  // device pointers: the caller's stream as given (NULL = the legacy default stream, CUDA's own
+  // convention) so the call orders with the caller's work; host pointers: NULL = a private stream
+  const bool dev_ptrs0 = d->flags & B200SOXR_BATCH_DEVICE_PTRS;
+  cudaStream_t st = (cuda_stream || dev_ptrs0) ? static_cast<cudaStream_t>(cuda_stream) : ws->stream;
   const char *e = nullptr;
 
   IoLayout li{d->dtype, d->n_clips, d->channels, d->in_clip_stride, d->in_frame_stride, d->in_chan_stride};
@@ -490,12 +502,12 @@ b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *d, void co
       od.p = dev_out; od.dtype = d->dtype; od.channels = d->channels;
       od.clip_stride = d->out_clip_stride; od.frame_stride = d->out_frame_stride; od.chan_stride = d->out_chan_stride;
       od.base = 0;
-      if ((e = run_range(*dp, xin, long(d->ilen), n_sig, 0, long(total), od, ws, st))) return e;
+      if ((e = run_range(*dp, xin, long(d->ilen), n_sig, d->channels, 0, long(total), od, ws, st))) return e;
     } else {
       const size_t ys = (total + 63) & ~size_t(63);
       if ((e = ws->y.reserve(ys * n_sig * esz))) return e;
       const SigDesc yd = planar_desc(ws->y.p, dp->is_double, ys, 0, 0, 0);
-      if ((e = run_range(*dp, xin, long(d->ilen), n_sig, 0, long(total), yd, ws, st))) return e;
+      if ((e = run_range(*dp, xin, long(d->ilen), n_sig, d->channels, 0, long(total), yd, ws, st))) return e;
 
       DitherCfg dc;
       dc.enabled = d->dtype == B200SOXR_INT16 && !(d->flags & B200SOXR_BATCH_NO_DITHER);
@@ -543,6 +555,11 @@ b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *d, void co
   if (!dev_ptrs) {
     if (out_span) B2_CUDA(cudaMemcpyAsync(out, dev_out, out_span * isz, cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
+  } else {
+    // asynchronous return is only safe when no pooled scratch buffer is still in use by queued work
+    const size_t fused_stages = dp->fft ? (dp->fft->fused_poly ? 2 : 1) : 0;
+    const bool scratch_free = d->dtype <= B200SOXR_FLOAT64 && fused_stages == dp->plan.stages.size();
+    if (!scratch_free) B2_CUDA(cudaStreamSynchronize(st));
   }
   return nullptr;
 }

@@ -99,9 +99,9 @@ const char *prepare_t(DevicePlan *dp, FftStageInfo &fi) {
   if (fi.fused_poly) {
     const Stage &ps = dp->plan.stages[fi.stage_index + 1];
     DevStage &pd = dp->stages[fi.stage_index + 1];
-    std::vector<R> tab((size_t(fi.pL) * fi.ncp * sizeof(R) + 15) / 16 * 16 / sizeof(R), R(0));
+    std::vector<R> tab((size_t(fi.pL) * fi.nrow * sizeof(R) + 15) / 16 * 16 / sizeof(R), R(0));
     for (int ph = 0; ph < fi.pL; ++ph)
-      for (int k = 0; k < fi.nc; ++k) tab[size_t(ph) * fi.ncp + k] = R(ps.table[size_t(ph) * fi.nc + k]);
+      for (int k = 0; k < fi.nc; ++k) tab[size_t(ph) * fi.nrow + k] = R(ps.table[size_t(ph) * fi.nc + k]);
     if ((e = upload_vec(tab, &pd.ptab))) return e;
   }
   return nullptr;
@@ -153,12 +153,20 @@ const char *launch_n(const FftStageInfo &fi, const FftKParams &P, long long n_it
   return "internal: fused FFT stage built for n in [512, 4096] only";
 }
 
+// stride of one output phase inside U: room for the 4-tap chunk over-read, even, and for L == 2
+// congruent to 8 mod 16 so that the two phase planes start half a bank-wheel apart
+int u_stride(const FftStageInfo &fi) {
+  int us = (fi.v_base + fi.delta + 4 + 1) & ~1;
+  if (fi.L == 2) while ((us & 15) != 8) us += 2;
+  return us;
+}
+
 size_t smem_for(const FftStageInfo &fi, size_t real_size) {
   const size_t csz = 2 * real_size;
   const size_t buf_elems = size_t(fi.n) + (fi.n >> 4) + (csz == 8 ? (fi.n >> 8) : (fi.n >> 7)) + 8;
-  const size_t us = size_t((fi.v_base + fi.delta + 1) & ~1);
+  const size_t us = size_t(u_stride(fi));
   size_t bytes = (buf_elems + size_t(fi.L) * us) * csz;
-  if (fi.fused_poly) bytes += (size_t(fi.pL) * fi.ncp * real_size + 15) / 16 * 16;
+  if (fi.fused_poly) bytes += (size_t(fi.pL) * fi.nrow * real_size + 15) / 16 * 16;
   return bytes;
 }
 
@@ -209,7 +217,8 @@ const char *fft_stage_prepare(DevicePlan *dp) {
       fi->p_at0 = ps.at0_int;
       fi->p_pre = ps.dev_preload;
       fi->nc = ps.num_coefs;
-      fi->ncp = ps.num_coefs | 1;
+      fi->ncp = (ps.num_coefs + 3) & ~3;   // rows zero-padded to whole 4-tap chunks
+      fi->nrow = fi->ncp | 1;              // odd row stride: phases spread over all banks
       fi->delta = (ps.num_coefs - 1 + L - 1) / L;
       fi->fused_poly = true;
       const size_t need = smem_for(*fi, dp->is_double ? 8 : 4);
@@ -251,14 +260,17 @@ RangeLH fft_stage_input_range(const FftStageInfo &fi, long lo, long hi) {
 }
 
 const char *fft_stage_run(const DevicePlan &dp, const FftStageInfo &fi, const SigDesc &in, const SigDesc &out,
-                          long o0, long o1, unsigned n_sig, cudaStream_t st) {
+                          long o0, long o1, unsigned n_sig, unsigned group, cudaStream_t st) {
   if (o1 <= o0 || !n_sig) return nullptr;
   const DevStage &ds = dp.stages[fi.stage_index];
   FftKParams P;
   P.in = in;
   P.out = out;
   P.n_sig = n_sig;
-  P.n_pairs = (n_sig + 1) / 2;
+  if (!group || n_sig % group) group = n_sig;
+  P.group = group;
+  P.ppg = (group + 1) / 2;
+  P.n_pairs = (n_sig / group) * P.ppg;
   P.b_first = block_of(fi, o0);
   P.n_blocks = int(block_of(fi, o1 - 1) - P.b_first + 1);
   P.o0 = o0;
@@ -266,18 +278,18 @@ const char *fft_stage_run(const DevicePlan &dp, const FftStageInfo &fi, const Si
   P.k0 = fi.k0;
   P.v_base = fi.v_base;
   P.delta = fi.delta;
-  P.us = (fi.v_base + fi.delta + 1) & ~1;
+  P.us = u_stride(fi);
   const size_t csz = dp.is_double ? 16 : 8;
   P.spec = ds.spec.p;
   P.tw2 = ds.twid.p;
   P.tw3 = static_cast<const char *>(ds.twid.p) + size_t(16) * (fi.n / 256) * csz;
   P.edge = ds.edge.p;
   P.ptab = nullptr;
-  P.pL = fi.pL; P.pM = fi.pM; P.p_at0 = fi.p_at0; P.p_pre = fi.p_pre; P.nc = fi.nc; P.ncp = fi.ncp;
+  P.pL = fi.pL; P.pM = fi.pM; P.p_at0 = fi.p_at0; P.p_pre = fi.p_pre; P.nc = fi.nc; P.ncp = fi.ncp; P.nrow = fi.nrow;
   P.ptab_bytes = 0;
   if (fi.fused_poly) {
     P.ptab = dp.stages[fi.stage_index + 1].ptab.p;
-    P.ptab_bytes = unsigned((size_t(fi.pL) * fi.ncp * (dp.is_double ? 8 : 4) + 15) / 16 * 16);
+    P.ptab_bytes = unsigned((size_t(fi.pL) * fi.nrow * (dp.is_double ? 8 : 4) + 15) / 16 * 16);
   }
   const long long n_items = (long long)P.n_pairs * P.n_blocks;
   if (dp.is_double)

@@ -45,7 +45,7 @@ struct FftStageInfo {
   long k0 = 0;                   // input index of point 0 (phase 0) of block 0
   int span = 0, v_base = 0;      // valid outputs per block and phase = n - span
   int delta = 0;                 // halo (base-rate samples) kept in front of a block for the poly stage
-  int pL = 1, pM = 1, p_at0 = 0, p_pre = 0, nc = 0, ncp = 0;
+  int pL = 1, pM = 1, p_at0 = 0, p_pre = 0, nc = 0, ncp = 0, nrow = 0;
   size_t smem_bytes = 0;
   int threads = 0;
   int max_ctas_per_sm = 1;
@@ -54,13 +54,14 @@ struct FftStageInfo {
 struct FftKParams {
   SigDesc in, out;
   unsigned n_sig, n_pairs;
+  unsigned group, ppg;           // signals per clip; pairs per clip = (group + 1) / 2 (pairs never span clips)
   long b_first;
   int n_blocks;
   long o0, o1;
   long k0;
   int v_base, delta, us;         // us: stride of one output phase inside U
   const void *spec, *tw2, *tw3, *edge, *ptab;
-  int pL, pM, p_at0, p_pre, nc, ncp;
+  int pL, pM, p_at0, p_pre, nc, ncp, nrow;   // ncp: taps looped (multiple of 4); nrow: odd row stride
   unsigned ptab_bytes;
 };
 
@@ -78,10 +79,6 @@ template <typename R> __device__ __forceinline__ void st_as(void *p, int dtype, 
   if (dtype == 0) static_cast<float *>(p)[idx] = float(v);
   else static_cast<double *>(p)[idx] = double(v);
 }
-
-template <int BYTES> __device__ __forceinline__ int phys(int p);
-template <> __device__ __forceinline__ int phys<8>(int p) { return p + (p >> 4) + (p >> 8); }
-template <> __device__ __forceinline__ int phys<16>(int p) { return p + (p >> 4) + (p >> 7); }
 
 __host__ __device__ inline long long ceil_div_ll(long long a, long long b) {   // b > 0
   return a >= 0 ? (a + b - 1) / b : -((-a) / b);
@@ -115,14 +112,14 @@ struct PairIn {
 };
 
 template <typename R>
-__device__ __forceinline__ PairIn<R> make_pair_in(const SigDesc &d, unsigned pair, unsigned n_sig) {
+__device__ __forceinline__ PairIn<R> make_pair_in(const SigDesc &d, unsigned s0, bool has1) {
   PairIn<R> pi;
-  const unsigned s0 = 2 * pair, s1 = s0 + 1;
+  const unsigned s1 = s0 + 1;
   pi.p = d.p;
   pi.dtype = d.dtype;
   pi.fs = d.frame_stride;
   pi.off0 = (long long)(s0 / d.channels) * d.clip_stride + (long long)(s0 % d.channels) * d.chan_stride - d.base * d.frame_stride;
-  pi.has1 = s1 < n_sig;
+  pi.has1 = has1;
   pi.off1 = pi.has1 ? (long long)(s1 / d.channels) * d.clip_stride + (long long)(s1 % d.channels) * d.chan_stride - d.base * d.frame_stride
                     : pi.off0;
   pi.vlo = d.vlo;
@@ -172,6 +169,77 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src, un
                : "memory");
 }
 
+// Padded shared-memory index.  phys is a sum of shifts, so for x, y occupying
+// disjoint bit ranges phys(x + y) == phys(x) + phys(y): every access below is
+// "per-thread base (computed once per CTA) + compile-time constant".
+template <int BYTES> __host__ __device__ constexpr int physc(int p) {
+  return BYTES == 8 ? p + (p >> 4) + (p >> 8) : p + (p >> 4) + (p >> 7);
+}
+
+// ---------------------------------------------------------------------------
+// K3 out of shared memory: outputs [n_lo, n_hi) of one block, one output per
+// thread per trip.  U holds the block's FFT-stage output (planar by phase r).
+// The tap loop runs in chunks of 4 (table rows are zero-padded to ncp = 4*nq).
+// ---------------------------------------------------------------------------
+template <typename R, int L, int T>
+__device__ __forceinline__ void poly_emit(const FftKParams &P, const typename V2<R>::type *__restrict__ U,
+                                          const R *__restrict__ tab, long n_lo, long n_hi, long ubase, int t,
+                                          long long ooff0, long long ooff1, bool has1, bool ovec) {
+  typedef typename V2<R>::type C;
+  if (n_lo + t >= n_hi) return;
+  const long long at = (long long)P.p_at0 + (long long)(n_lo + t) * P.pM;
+  long div = long(at / P.pL);
+  int rem = int(at % P.pL);
+  const int dstep = int((long long)T * P.pM / P.pL), rstep = int((long long)T * P.pM % P.pL);
+  const int nq = P.ncp >> 2;
+  for (long nn = n_lo + t; nn < n_hi; nn += T) {
+    const int rel = int(div - P.p_pre - ubase);
+    const R *__restrict__ c = tab + rem * P.nrow;
+    R ax = R(0), ay = R(0);
+    if (L == 1) {
+      const C *__restrict__ A = U + rel;
+#pragma unroll 2
+      for (int q = 0; q < nq; ++q) {
+        const R c0 = c[4 * q], c1 = c[4 * q + 1], c2 = c[4 * q + 2], c3 = c[4 * q + 3];
+        const C u0 = A[4 * q], u1 = A[4 * q + 1], u2 = A[4 * q + 2], u3 = A[4 * q + 3];
+        ax = fma(c0, u0.x, ax); ay = fma(c0, u0.y, ay);
+        ax = fma(c1, u1.x, ax); ay = fma(c1, u1.y, ay);
+        ax = fma(c2, u2.x, ax); ay = fma(c2, u2.y, ay);
+        ax = fma(c3, u3.x, ax); ay = fma(c3, u3.y, ay);
+      }
+    } else if (L == 2) {
+      // tap k reads U index rel + k: even taps from plane (rel & 1), odd taps from the other one
+      const int par = rel & 1, h = rel >> 1;
+      const C *__restrict__ A = U + par * P.us + h;
+      const C *__restrict__ B = U + (1 - par) * P.us + h + par;
+#pragma unroll 2
+      for (int q = 0; q < nq; ++q) {
+        const R c0 = c[4 * q], c1 = c[4 * q + 1], c2 = c[4 * q + 2], c3 = c[4 * q + 3];
+        const C u0 = A[2 * q], u1 = B[2 * q], u2 = A[2 * q + 1], u3 = B[2 * q + 1];
+        ax = fma(c0, u0.x, ax); ay = fma(c0, u0.y, ay);
+        ax = fma(c1, u1.x, ax); ay = fma(c1, u1.y, ay);
+        ax = fma(c2, u2.x, ax); ay = fma(c2, u2.y, ay);
+        ax = fma(c3, u3.x, ax); ay = fma(c3, u3.y, ay);
+      }
+    } else {
+      for (int k = 0; k < P.nc; ++k) {
+        const int idx = rel + k;
+        const C u = U[(idx % L) * P.us + idx / L];
+        const R cv = c[k];
+        ax = fma(cv, u.x, ax);
+        ay = fma(cv, u.y, ay);
+      }
+    }
+    C o;
+    o.x = ax;
+    o.y = ay;
+    store_pair<R>(P.out, ooff0, ooff1, has1, ovec, nn, o);
+    div += dstep;
+    rem += rstep;
+    if (rem >= P.pL) { rem -= P.pL; ++div; }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // The kernel.  R: engine real type.  n = 2^LOG2N.  L, M: stage ratio.  POLY: a
 // rational polyphase stage (vpoly0) consumes the block from shared memory.
@@ -191,8 +259,8 @@ __global__ void __launch_bounds__((1 << LOG2N) / 16) k_fft_stage(const FftKParam
 
   const int t = threadIdx.x;
   const C *__restrict__ tw2 = static_cast<const C *>(P.tw2);
-  const C *__restrict__ tw3 = static_cast<const C *>(P.tw3);
-  const C *__restrict__ spec = static_cast<const C *>(P.spec);
+  const C *__restrict__ tw3 = static_cast<const C *>(P.tw3) + t;
+  const C *__restrict__ spec = static_cast<const C *>(P.spec) + t;
 
   if (POLY) {   // K8's table: staged once per CTA with a TMA bulk copy, waited for before the first use
     if (t == 0) {
@@ -206,16 +274,42 @@ __global__ void __launch_bounds__((1 << LOG2N) / 16) k_fft_stage(const FftKParam
     }
   }
   bool tab_ready = !POLY;
+  if (POLY) {   // slack behind each phase plane: over-read by the last 4-tap chunk with zero coefficients
+    const int pad0 = P.delta + P.v_base, npad = P.us - pad0;
+    for (int i = t; i < L * npad; i += T) {
+      C z;
+      z.x = R(0);
+      z.y = R(0);
+      U[(i / npad) * P.us + pad0 + i % npad] = z;
+    }
+  }
 
-  const int j2 = t % R1, G2 = t / R1, e0 = G2 * T + j2;
+  // per-thread shared-memory bases of the three exchange patterns (see physc)
+  const int j2 = t % R1, G2 = t / R1;
+  C *const b2p = buf + physc<EB>(G2 * T + j2);     // pass 2: + physc(R1 * m)
+  C *const b3p = buf + physc<EB>(t);               // pass 3: + physc(T * m)
+  C *b1p[NB1];                                     // pass 1: + q1
+#pragma unroll
+  for (int u = 0; u < NB1; ++u) {
+    const int g = t + T * u;
+    b1p[u] = buf + physc<EB>(R1 * (g >> 4) + T * (g & 15));
+  }
+  tw2 += j2;
+
   const long LV = long(L) * P.v_base;
   const long long n_items = (long long)P.n_pairs * P.n_blocks;
 
   for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
     const unsigned pair = unsigned(item / P.n_blocks);
     const long b = P.b_first + long(item % P.n_blocks);
-    const PairIn<R> pin = make_pair_in<R>(P.in, pair, P.n_sig);
+    // signal 2cp of clip `clip` in the real part, 2cp+1 (if the clip has it) in the imaginary part
+    const unsigned clip = pair / P.ppg, cp = pair % P.ppg;
+    const unsigned s0 = clip * P.group + 2 * cp, s1 = s0 + 1;
+    const bool has1 = 2 * cp + 1 < P.group;
+    const PairIn<R> pin = make_pair_in<R>(P.in, s0, has1);
     const long k0 = P.k0 + b * long(M) * P.v_base;   // input index of point 0, phase 0
+    // the whole block (and its halo-correction reads) inside the valid input: no per-sample checks
+    const bool interior = pin.vec && k0 - long(M) * P.delta >= pin.vlo && k0 + long(M) * N <= pin.vhi;
 
     // ---- halo correction terms (threads < L*delta), see file header -------------
     C corr;
@@ -239,10 +333,24 @@ __global__ void __launch_bounds__((1 << LOG2N) / 16) k_fft_stage(const FftKParam
 #pragma unroll
     for (int s = 0; s < M; ++s) {
       C v[16];
+      if (interior) {
+        const float2 *__restrict__ src =
+            reinterpret_cast<const float2 *>(static_cast<const float *>(pin.p) + pin.off0 + (k0 + s) * pin.fs) ;
+        const long long st2 = (long long)M * (pin.fs >> 1);   // float2 elements per block point
 #pragma unroll
-      for (int u = 0; u < NB1; ++u)
+        for (int u = 0; u < NB1; ++u)
 #pragma unroll
-        for (int m1 = 0; m1 < R1; ++m1) v[u * R1 + m1] = pin.load(k0 + long(M) * (t + T * u + 256 * m1) + s);
+          for (int m1 = 0; m1 < R1; ++m1) {
+            const float2 x = src[(long long)(t + T * u + 256 * m1) * st2];
+            v[u * R1 + m1].x = R(x.x);
+            v[u * R1 + m1].y = R(x.y);
+          }
+      } else {
+#pragma unroll
+        for (int u = 0; u < NB1; ++u)
+#pragma unroll
+          for (int m1 = 0; m1 < R1; ++m1) v[u * R1 + m1] = pin.load(k0 + long(M) * (t + T * u + 256 * m1) + s);
+      }
       __syncthreads();   // buf (and U) free: previous item / phase finished reading
 #pragma unroll
       for (int u = 0; u < NB1; ++u) {
@@ -250,23 +358,22 @@ __global__ void __launch_bounds__((1 << LOG2N) / 16) k_fft_stage(const FftKParam
 #pragma unroll
         for (int m1 = 0; m1 < R1; ++m1) a[m1] = v[u * R1 + m1];
         Dft<R1>::template run<false>(a);
-        const int g = t + T * u, base = R1 * (g >> 4) + T * (g & 15);
 #pragma unroll
-        for (int q1 = 0; q1 < R1; ++q1) buf[phys<EB>(base + q1)] = a[q1];
+        for (int q1 = 0; q1 < R1; ++q1) b1p[u][q1] = a[q1];
       }
       __syncthreads();
 #pragma unroll
-      for (int m = 0; m < 16; ++m) v[m] = buf[phys<EB>(e0 + R1 * m)];
+      for (int m = 0; m < 16; ++m) v[m] = b2p[physc<EB>(R1 * m)];
 #pragma unroll
-      for (int m = 1; m < 16; ++m) v[m] = cmul(v[m], tw2[m * R1 + j2]);
+      for (int m = 1; m < 16; ++m) v[m] = cmul(v[m], tw2[m * R1]);
       Dft<16>::template run<false>(v);
 #pragma unroll
-      for (int q = 0; q < 16; ++q) buf[phys<EB>(e0 + R1 * q)] = v[q];
+      for (int q = 0; q < 16; ++q) b2p[physc<EB>(R1 * q)] = v[q];
       __syncthreads();
 #pragma unroll
-      for (int m = 0; m < 16; ++m) v[m] = buf[phys<EB>(t + T * m)];
+      for (int m = 0; m < 16; ++m) v[m] = b3p[physc<EB>(T * m)];
 #pragma unroll
-      for (int m = 1; m < 16; ++m) v[m] = cmul(v[m], tw3[m * T + t]);
+      for (int m = 1; m < 16; ++m) v[m] = cmul(v[m], tw3[m * T]);
       Dft<16>::template run<false>(v);
 #pragma unroll
       for (int q = 0; q < 16; ++q) Z[s][q] = v[q];
@@ -278,10 +385,10 @@ __global__ void __launch_bounds__((1 << LOG2N) / 16) k_fft_stage(const FftKParam
       C v[16];
 #pragma unroll
       for (int q = 0; q < 16; ++q) {
-        C acc = cmul(Z[0][q], spec[((r * M + 0) * 16 + q) * T + t]);
+        C acc = cmul(Z[0][q], spec[((r * M + 0) * 16 + q) * T]);
 #pragma unroll
         for (int s = 1; s < M; ++s) {
-          const C e = cmul(Z[s][q], spec[((r * M + s) * 16 + q) * T + t]);
+          const C e = cmul(Z[s][q], spec[((r * M + s) * 16 + q) * T]);
           acc.x += e.x;
           acc.y += e.y;
         }
@@ -289,37 +396,45 @@ __global__ void __launch_bounds__((1 << LOG2N) / 16) k_fft_stage(const FftKParam
       }
       Dft<16>::template run<true>(v);
 #pragma unroll
-      for (int m = 1; m < 16; ++m) v[m] = cmulc(v[m], tw3[m * T + t]);
+      for (int m = 1; m < 16; ++m) v[m] = cmulc(v[m], tw3[m * T]);
       __syncthreads();   // previous readers of buf are done
 #pragma unroll
-      for (int m = 0; m < 16; ++m) buf[phys<EB>(t + T * m)] = v[m];
+      for (int m = 0; m < 16; ++m) b3p[physc<EB>(T * m)] = v[m];
       __syncthreads();
 #pragma unroll
-      for (int q = 0; q < 16; ++q) v[q] = buf[phys<EB>(e0 + R1 * q)];
+      for (int q = 0; q < 16; ++q) v[q] = b2p[physc<EB>(R1 * q)];
       Dft<16>::template run<true>(v);
 #pragma unroll
-      for (int m = 1; m < 16; ++m) v[m] = cmulc(v[m], tw2[m * R1 + j2]);
+      for (int m = 1; m < 16; ++m) v[m] = cmulc(v[m], tw2[m * R1]);
 #pragma unroll
-      for (int m = 0; m < 16; ++m) buf[phys<EB>(e0 + R1 * m)] = v[m];
+      for (int m = 0; m < 16; ++m) b2p[physc<EB>(R1 * m)] = v[m];
       __syncthreads();
+      C *const Ur = U + r * P.us + P.delta;
 #pragma unroll
       for (int u = 0; u < NB1; ++u) {
         C a[R1];
-        const int g = t + T * u, base = R1 * (g >> 4) + T * (g & 15);
+        const int g = t + T * u;
 #pragma unroll
-        for (int q1 = 0; q1 < R1; ++q1) a[q1] = buf[phys<EB>(base + q1)];
+        for (int q1 = 0; q1 < R1; ++q1) a[q1] = b1p[u][q1];
         Dft<R1>::template run<true>(a);
 #pragma unroll
         for (int m1 = 0; m1 < R1; ++m1) {
           const int i = g + 256 * m1;            // block-local output index i'
-          if (i < P.v_base) U[r * P.us + P.delta + i] = a[m1];
-          else if (POLY && i >= N - P.delta) U[r * P.us + i - (N - P.delta)] = a[m1];   // circular tail = halo (uncorrected)
+          if (i < P.v_base) Ur[i] = a[m1];
+          else if (POLY && i >= N - P.delta) Ur[i - N] = a[m1];   // circular tail = halo (uncorrected)
         }
       }
     }
     __syncthreads();
 
     const long J0 = b * LV;   // first valid output of this block (output-rate index of the FFT stage)
+    const long long ooff0 = (long long)(s0 / P.out.channels) * P.out.clip_stride +
+                            (long long)(s0 % P.out.channels) * P.out.chan_stride - P.out.base * P.out.frame_stride;
+    const long long ooff1 = has1 ? (long long)(s1 / P.out.channels) * P.out.clip_stride +
+                                       (long long)(s1 % P.out.channels) * P.out.chan_stride - P.out.base * P.out.frame_stride
+                                 : ooff0;
+    const bool ovec = P.out.dtype == 0 && has1 && ooff1 == ooff0 + 1 && !(ooff0 & 1) && !(P.out.frame_stride & 1) &&
+                      !(reinterpret_cast<unsigned long long>(P.out.p) & 7);
     if (POLY) {
       // halo: add the wrap-around correction; the intermediate does not exist before index 0 (cr.c:487-490)
       if (t < L * P.delta) {
@@ -335,59 +450,14 @@ __global__ void __launch_bounds__((1 << LOG2N) / 16) k_fft_stage(const FftKParam
         tab_ready = true;
       }
       __syncthreads();
-
-      // ---- K3: rational polyphase stage out of shared memory ----------------------
       const long long Q0 = (long long)J0 - P.nc + 1 + P.p_pre, Q1 = Q0 + LV;
       long n_lo = b == 0 ? 0 : long(max(0LL, ceil_div_ll(Q0 * P.pL - P.p_at0, P.pM)));
       long n_hi = long(max(0LL, ceil_div_ll(Q1 * P.pL - P.p_at0, P.pM)));
       n_lo = max(n_lo, P.o0);
       n_hi = min(n_hi, P.o1);
-      const unsigned s0 = 2 * pair, s1 = s0 + 1;
-      const bool has1 = s1 < P.n_sig;
-      const long long ooff0 = (long long)(s0 / P.out.channels) * P.out.clip_stride +
-                              (long long)(s0 % P.out.channels) * P.out.chan_stride - P.out.base * P.out.frame_stride;
-      const long long ooff1 = has1 ? (long long)(s1 / P.out.channels) * P.out.clip_stride +
-                                         (long long)(s1 % P.out.channels) * P.out.chan_stride - P.out.base * P.out.frame_stride
-                                   : ooff0;
-      const bool ovec = P.out.dtype == 0 && has1 && ooff1 == ooff0 + 1 && !(ooff0 & 1) && !(P.out.frame_stride & 1) &&
-                        !(reinterpret_cast<unsigned long long>(P.out.p) & 7);
-      const long ubase = J0 - long(L) * P.delta;   // output-rate index of U's first element
-      if (n_lo + t < n_hi) {
-        const long long at = (long long)P.p_at0 + (long long)(n_lo + t) * P.pM;
-        long div = long(at / P.pL);
-        int rem = int(at % P.pL);
-        const int dstep = int((long long)T * P.pM / P.pL), rstep = int((long long)T * P.pM % P.pL);
-        for (long nn = n_lo + t; nn < n_hi; nn += T) {
-          const int rel = int(div - P.p_pre - ubase);
-          const R *__restrict__ c = tab + rem * P.ncp;
-          R ax = R(0), ay = R(0);
-          for (int k = 0; k < P.nc; ++k) {
-            const int idx = rel + k;
-            const C u = U[(idx % L) * P.us + idx / L];
-            const R cv = c[k];
-            ax = fma(cv, u.x, ax);
-            ay = fma(cv, u.y, ay);
-          }
-          C o;
-          o.x = ax;
-          o.y = ay;
-          store_pair<R>(P.out, ooff0, ooff1, has1, ovec, nn, o);
-          div += dstep;
-          rem += rstep;
-          if (rem >= P.pL) { rem -= P.pL; ++div; }
-        }
-      }
+      poly_emit<R, L, T>(P, U, tab, n_lo, n_hi, J0 - long(L) * P.delta, t, ooff0, ooff1, has1, ovec);
     } else {
       // ---- emit the block: out[J0 + L i' + r], interleaving the L output phases ----
-      const unsigned s0 = 2 * pair, s1 = s0 + 1;
-      const bool has1 = s1 < P.n_sig;
-      const long long ooff0 = (long long)(s0 / P.out.channels) * P.out.clip_stride +
-                              (long long)(s0 % P.out.channels) * P.out.chan_stride - P.out.base * P.out.frame_stride;
-      const long long ooff1 = has1 ? (long long)(s1 / P.out.channels) * P.out.clip_stride +
-                                         (long long)(s1 % P.out.channels) * P.out.chan_stride - P.out.base * P.out.frame_stride
-                                   : ooff0;
-      const bool ovec = P.out.dtype == 0 && has1 && ooff1 == ooff0 + 1 && !(ooff0 & 1) && !(P.out.frame_stride & 1) &&
-                        !(reinterpret_cast<unsigned long long>(P.out.p) & 7);
       const long lo = max(J0, P.o0), hi = min(J0 + LV, P.o1);
       for (long j = lo + t; j < hi; j += T) {
         const int idx = int(j - J0);
@@ -407,7 +477,8 @@ struct RangeLH { long lo, hi; };
 // Input range (of the stage feeding the fused launch) needed for final outputs [lo, hi) of the launch.
 RangeLH fft_stage_input_range(const FftStageInfo &fi, long lo, long hi);
 
+// `group`: signals per clip; two signals share a complex FFT only inside one clip.
 const char *fft_stage_run(const DevicePlan &dp, const FftStageInfo &fi, const SigDesc &in, const SigDesc &out,
-                          long o0, long o1, unsigned n_sig, cudaStream_t st);
+                          long o0, long o1, unsigned n_sig, unsigned group, cudaStream_t st);
 
 }  // namespace b2

@@ -83,15 +83,19 @@ std::map<PlanKey, std::shared_ptr<DevicePlan>> g_plans;
 }  // namespace
 
 Workspace *acquire_workspace() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
   {
     std::lock_guard<std::mutex> l(g_ws_mu);
-    if (!g_ws_free.empty()) {
-      Workspace *w = g_ws_free.back();
-      g_ws_free.pop_back();
-      return w;
-    }
+    for (size_t i = g_ws_free.size(); i-- > 0;)
+      if (g_ws_free[i]->device == dev) {   // streams and buffers belong to one device
+        Workspace *w = g_ws_free[i];
+        g_ws_free.erase(g_ws_free.begin() + long(i));
+        return w;
+      }
   }
   Workspace *w = new Workspace();
+  w->device = dev;
   if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess) w->stream = nullptr;
   return w;
 }
@@ -346,7 +350,7 @@ const char *run_stage_generic(const DevicePlan &dp, size_t si, SigIn<T> in, SigO
 }
 
 template <typename T>
-const char *run_range_t(const DevicePlan &dp, const SigDesc &in0, long n_in_total, unsigned n_sig, long o0, long o1,
+const char *run_range_t(const DevicePlan &dp, const SigDesc &in0, long n_in_total, unsigned n_sig, unsigned group, long o0, long o1,
                         const SigDesc &out0, Workspace *ws, cudaStream_t st) {
   const size_t S = dp.plan.stages.size();
   if (o1 <= o0 || !n_sig) return nullptr;
@@ -397,7 +401,7 @@ const char *run_range_t(const DevicePlan &dp, const SigDesc &in0, long n_in_tota
       dst = planar_desc(dst_buf->p, sizeof(T) == 8, stride, ln.r.lo, std::max(0L, ln.r.lo), ln.r.hi);
     }
     const char *e;
-    if (ln.fft) e = fft_stage_run(dp, *dp.fft, cur, dst, ln.r.lo, ln.r.hi, n_sig, st);
+    if (ln.fft) e = fft_stage_run(dp, *dp.fft, cur, dst, ln.r.lo, ln.r.hi, n_sig, group, st);
     else {
       SigIn<T> gi{static_cast<const T *>(cur.p), size_t(cur.clip_stride), cur.base, cur.vlo, cur.vhi};
       SigOut<T> go{static_cast<T *>(dst.p), size_t(dst.clip_stride), dst.base};
@@ -412,10 +416,10 @@ const char *run_range_t(const DevicePlan &dp, const SigDesc &in0, long n_in_tota
 }
 }  // namespace
 
-const char *run_range(const DevicePlan &dp, const SigDesc &in, long n_in_total, unsigned n_sig, long o0, long o1,
-                      const SigDesc &out, Workspace *ws, cudaStream_t stream) {
-  return dp.is_double ? run_range_t<double>(dp, in, n_in_total, n_sig, o0, o1, out, ws, stream)
-                      : run_range_t<float>(dp, in, n_in_total, n_sig, o0, o1, out, ws, stream);
+const char *run_range(const DevicePlan &dp, const SigDesc &in, long n_in_total, unsigned n_sig, unsigned group,
+                      long o0, long o1, const SigDesc &out, Workspace *ws, cudaStream_t stream) {
+  return dp.is_double ? run_range_t<double>(dp, in, n_in_total, n_sig, group, o0, o1, out, ws, stream)
+                      : run_range_t<float>(dp, in, n_in_total, n_sig, group, o0, o1, out, ws, stream);
 }
 
 long history_needed_from(const DevicePlan &dp, long o) {

@@ -67,6 +67,7 @@ const char *get_device_plan(double io_ratio, const QSpec &q, const RSpec &r, dou
 // Per-call scratch: reused across calls through a pool so concurrent callers
 // (the reference's thread-pool tests) never share buffers.
 struct Workspace {
+  int device = 0;
   cudaStream_t stream = nullptr;
   DevBuf in_stage, out_stage, x, y, t0, t1, seeds, blocks, misc;
   PinnedBuf pin_in, pin_out, pin_misc;
@@ -105,8 +106,9 @@ inline SigDesc planar_desc(void *p, bool is_double, size_t stride, long base, lo
 // logical indices [in.vlo, in.vhi) (zero outside; n_in_total < 0 means more input
 // may still arrive, so reading beyond in.vhi is an error).  `out` is a float32 /
 // float64 destination in any layout (element 0 of a signal == output out.base).
-const char *run_range(const DevicePlan &dp, const SigDesc &in, long n_in_total, unsigned n_sig, long o0, long o1,
-                      const SigDesc &out, Workspace *ws, cudaStream_t stream);
+// `group` = channels per clip (n_sig is a multiple of it).
+const char *run_range(const DevicePlan &dp, const SigDesc &in, long n_in_total, unsigned n_sig, unsigned group,
+                      long o0, long o1, const SigDesc &out, Workspace *ws, cudaStream_t stream);
 
 // Lowest input index any output >= o can still depend on (for history trimming).
 long history_needed_from(const DevicePlan &dp, long o);

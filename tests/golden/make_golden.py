@@ -115,7 +115,7 @@ def main():
 
     streams = {}
     for name, (seed, n, ch, dtype, ir, orate, q, chunk) in STREAM_CASES.items():
-        x = make_input(seed, (n, ch), dtype, 1.0)
+        x = make_input(seed, (n, ch), dtype, 5000.0 if np.dtype(dtype).kind == 'i' else 1.0)
         rs = R.RefStream(ir, orate, ch, dtype, q)
         counts, delays = [], []
         for idx in range(0, n, chunk):

@@ -180,14 +180,21 @@ def test_stream_length(in_rate, out_rate, chunk_size, length, dtype):
 @pytest.mark.parametrize("name", sorted(STREAMS))
 def test_stream_counts_delays_match_reference(name):
     s = STREAMS[name]
-    x = make_input(s['seed'], (s['frames'], s['channels']), s['dtype'], 1.0)
+    is_int = np.dtype(s['dtype']).kind == 'i'
+    x = make_input(s['seed'], (s['frames'], s['channels']), s['dtype'], 5000.0 if is_int else 1.0)
     y, counts, delays = _stream(x, s['in_rate'], s['out_rate'], s['chunk'], s['dtype'], s['quality'])
     assert counts == s['counts']
     assert np.allclose(delays, s['delays'], rtol=0, atol=1e-9)
     orc = O.resample_f64(x, s['in_rate'], s['out_rate'], Q[s['quality']])
     assert y.shape == orc.shape
-    assert rms(y - orc) <= TOL_F32
-    assert np.all(y == soxr.resample(x, s['in_rate'], s['out_rate'], s['quality']))
+    if is_int:
+        # rounding (.5) + TPDF dither (< 1) on top of the engine's float result; the reference's
+        # own stream-vs-oneshot tolerance for ints is atol=2 (tests/test_resample.py:130)
+        assert np.abs(y - orc).max() <= 1.5 + 1e-3 * np.abs(orc).max()
+        assert np.allclose(y, soxr.resample(x, s['in_rate'], s['out_rate'], s['quality']), atol=2)
+    else:
+        assert rms(y - orc) <= TOL_F32
+        assert np.all(y == soxr.resample(x, s['in_rate'], s['out_rate'], s['quality']))
 
 
 @pytest.mark.parametrize('in_rate, out_rate', [(48000, 22050), (8000, 48000)])
