@@ -89,7 +89,7 @@ B200SOXR_API char const *b200soxr_version(void);
 
 /* ---- stream handle API: soxr_create / soxr_process / soxr_delay /
  *      soxr_num_clips / soxr_engine / soxr_clear / soxr_delete
- *      (libsoxr/src/soxr.h:93-203; soxr.c:367-486,761-813,519-523,156-159,149-152,
+ *      (libsoxr/src/soxr.h:101-179; soxr.c:367-486,761-813,519-523,156-159,149-152,
  *       609-628,601-605).  `in`/`out` are HOST pointers unless the handle was
  *      created with B200SOXR_RT_DEVICE_IO in runtime_spec.flags. ---------------- */
 #define B200SOXR_RT_DEVICE_IO 0x100ul   /* extension: in/out of process() are device pointers */
@@ -108,7 +108,7 @@ B200SOXR_API char const *b200soxr_engine(b200soxr_t p);
 B200SOXR_API b200soxr_error_t b200soxr_clear(b200soxr_t p);
 B200SOXR_API void b200soxr_delete(b200soxr_t p);
 
-/* ---- one-shot: soxr_oneshot (soxr.h:164-174, soxr.c:816-838) --------------- */
+/* ---- one-shot: soxr_oneshot (soxr.h:188-198, soxr.c:816-838) --------------- */
 B200SOXR_API b200soxr_error_t b200soxr_oneshot(double input_rate, double output_rate, unsigned num_channels,
                                                void const *in, size_t ilen, size_t *idone,
                                                void *out, size_t olen, size_t *odone,
