@@ -5,6 +5,13 @@
 // radices keep each sample in registers for 3-4 butterfly levels between
 // shared-memory exchanges.  Outputs are in natural order.  INV selects the
 // conjugate (inverse, unnormalised) transform.
+//
+// float2 arithmetic uses Blackwell's packed f32x2 instructions (FADD2 / FMUL2 /
+// FFMA2 on sm_100a): same FLOP rate as scalar code but half the issue slots, and
+// the operand swizzles (.F32 broadcast, .LO_HI swap, .NP sign pattern) make a
+// complex multiply two instructions and a multiplication by -i free.  Everything
+// is phrased through  rot(a) = -i*a = (a.y, -a.x)  because that is the sign
+// pattern the hardware swizzle provides.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -14,34 +21,65 @@ template <typename R> struct V2;
 template <> struct V2<float> { typedef float2 type; };
 template <> struct V2<double> { typedef double2 type; };
 
-template <typename C> __host__ __device__ __forceinline__ C cadd(C a, C b) { C r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
-template <typename C> __host__ __device__ __forceinline__ C csub(C a, C b) { C r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
-// a * b
-template <typename C> __host__ __device__ __forceinline__ C cmul(C a, C b) {
-  C r;
-  r.x = a.x * b.x - a.y * b.y;
-  r.y = a.x * b.y + a.y * b.x;
-  return r;
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+#define B2_PACKED_F32 1
+#else
+#define B2_PACKED_F32 0
+#endif
+
+// ---- double2 (and host) : scalar -----------------------------------------------
+__host__ __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ double2 rot(double2 a) { return make_double2(a.y, -a.x); }   // -i * a
+// a + s * b, s real
+__host__ __device__ __forceinline__ double2 axpy(double s, double2 b, double2 a) {
+  return make_double2(fma(s, b.x, a.x), fma(s, b.y, a.y));
 }
-// a * conj(b)
-template <typename C> __host__ __device__ __forceinline__ C cmulc(C a, C b) {
-  C r;
-  r.x = a.x * b.x + a.y * b.y;
-  r.y = a.y * b.x - a.x * b.y;
-  return r;
+__host__ __device__ __forceinline__ double2 scale(double s, double2 a) { return make_double2(s * a.x, s * a.y); }
+
+// ---- float2 : packed on the device -----------------------------------------------
+__host__ __device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+#if B2_PACKED_F32
+  return __fadd2_rn(a, b);
+#else
+  return make_float2(a.x + b.x, a.y + b.y);
+#endif
 }
-// multiply by -i (forward) or +i (inverse)
-template <bool INV, typename C> __host__ __device__ __forceinline__ C mul_mi(C a) {
-  C r;
-  if (INV) { r.x = -a.y; r.y = a.x; } else { r.x = a.y; r.y = -a.x; }
-  return r;
+__host__ __device__ __forceinline__ float2 csub(float2 a, float2 b) {
+#if B2_PACKED_F32
+  return __fadd2_rn(a, make_float2(-b.x, -b.y));
+#else
+  return make_float2(a.x - b.x, a.y - b.y);
+#endif
 }
-// multiply by the constant (c - i s) forward, (c + i s) inverse
+__host__ __device__ __forceinline__ float2 rot(float2 a) { return make_float2(a.y, -a.x); }
+__host__ __device__ __forceinline__ float2 axpy(float s, float2 b, float2 a) {
+#if B2_PACKED_F32
+  return __ffma2_rn(make_float2(s, s), b, a);
+#else
+  return make_float2(fmaf(s, b.x, a.x), fmaf(s, b.y, a.y));
+#endif
+}
+__host__ __device__ __forceinline__ float2 scale(float s, float2 a) {
+#if B2_PACKED_F32
+  return __fmul2_rn(make_float2(s, s), a);
+#else
+  return make_float2(s * a.x, s * a.y);
+#endif
+}
+
+// a * b            = b.x * a - b.y * rot(a)
+template <typename C> __host__ __device__ __forceinline__ C cmul(C a, C b) { return axpy(-b.y, rot(a), scale(b.x, a)); }
+// a * conj(b)      = b.x * a + b.y * rot(a)
+template <typename C> __host__ __device__ __forceinline__ C cmulc(C a, C b) { return axpy(b.y, rot(a), scale(b.x, a)); }
+// a * (c - i s) forward, a * (c + i s) inverse  (c, s compile-time constants)
 template <bool INV, typename C, typename R> __host__ __device__ __forceinline__ C mul_w(C a, R c, R s) {
-  C r;
-  if (INV) { r.x = a.x * c - a.y * s; r.y = a.y * c + a.x * s; }
-  else { r.x = a.x * c + a.y * s; r.y = a.y * c - a.x * s; }
-  return r;
+  return axpy(INV ? -s : s, rot(a), scale(c, a));
+}
+// (a + w b, a - w b) with w = -i forward, +i inverse
+template <bool INV, typename C> __host__ __device__ __forceinline__ void addsub_rot(C a, C b, C &p, C &m) {
+  const C t = rot(b);
+  if (INV) { p = csub(a, t); m = cadd(a, t); } else { p = cadd(a, t); m = csub(a, t); }
 }
 
 template <bool INV, typename C> __host__ __device__ __forceinline__ void dft2(C &a, C &b) {
@@ -51,11 +89,10 @@ template <bool INV, typename C> __host__ __device__ __forceinline__ void dft2(C 
 }
 
 template <bool INV, typename C> __host__ __device__ __forceinline__ void dft4(C &a, C &b, C &c, C &d) {
-  const C t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), t3 = mul_mi<INV>(csub(b, d));
+  const C t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), t3 = csub(b, d);
   a = cadd(t0, t2);
   c = csub(t0, t2);
-  b = cadd(t1, t3);
-  d = csub(t1, t3);
+  addsub_rot<INV>(t1, t3, b, d);
 }
 
 template <int R> struct Dft;
@@ -74,14 +111,13 @@ template <> struct Dft<8> {
     const R h = R(0.70710678118654752440);
     dft4<INV>(v[0], v[2], v[4], v[6]);   // t[0][qb]
     dft4<INV>(v[1], v[3], v[5], v[7]);   // t[1][qb]
-    // t[1][qb] *= W8^qb
+    // X[qb + 4 qa] = t[0][qb] +- W8^qb t[1][qb]
     v[3] = mul_w<INV>(v[3], h, h);
-    v[5] = mul_mi<INV>(v[5]);
     v[7] = mul_w<INV>(v[7], -h, h);
-    // X[qb + 4 qa] = t[0][qb] +- t[1][qb]
     C x0 = cadd(v[0], v[1]), x4 = csub(v[0], v[1]);
     C x1 = cadd(v[2], v[3]), x5 = csub(v[2], v[3]);
-    C x2 = cadd(v[4], v[5]), x6 = csub(v[4], v[5]);
+    C x2, x6;
+    addsub_rot<INV>(v[4], v[5], x2, x6);   // W8^2 = -i
     C x3 = cadd(v[6], v[7]), x7 = csub(v[6], v[7]);
     v[0] = x0; v[1] = x1; v[2] = x2; v[3] = x3; v[4] = x4; v[5] = x5; v[6] = x6; v[7] = x7;
   }
@@ -97,12 +133,11 @@ template <> struct Dft<16> {
     dft4<INV>(v[1], v[5], v[9], v[13]);
     dft4<INV>(v[2], v[6], v[10], v[14]);
     dft4<INV>(v[3], v[7], v[11], v[15]);
-    // step 2: t[m0][qb] *= W16^(m0*qb)
+    // step 2: t[m0][qb] *= W16^(m0*qb)   (the W16^4 = -i factor of v[10] is folded into step 3)
     v[5] = mul_w<INV>(v[5], c1, s1);     // m0=1,qb=1 : W^1
     v[6] = mul_w<INV>(v[6], h, h);       // m0=2,qb=1 : W^2
     v[7] = mul_w<INV>(v[7], s1, c1);     // m0=3,qb=1 : W^3
     v[9] = mul_w<INV>(v[9], h, h);       // m0=1,qb=2 : W^2
-    v[10] = mul_mi<INV>(v[10]);          // m0=2,qb=2 : W^4
     v[11] = mul_w<INV>(v[11], -h, h);    // m0=3,qb=2 : W^6
     v[13] = mul_w<INV>(v[13], s1, c1);   // m0=1,qb=3 : W^3
     v[14] = mul_w<INV>(v[14], -h, h);    // m0=2,qb=3 : W^6
@@ -110,7 +145,15 @@ template <> struct Dft<16> {
     // step 3: for each qb, DFT4 over m0 -> X[qb + 4 qa] (in place at v[4 qb + qa])
     dft4<INV>(v[0], v[1], v[2], v[3]);
     dft4<INV>(v[4], v[5], v[6], v[7]);
-    dft4<INV>(v[8], v[9], v[10], v[11]);
+    {   // qb = 2 with c = W16^4 * v[10] = rot(v[10]) forward, -rot(v[10]) inverse
+      C &a = v[8], &b = v[9], &c = v[10], &d = v[11];
+      C t0, t1;
+      addsub_rot<INV>(a, c, t0, t1);     // a + w c, a - w c
+      const C t2 = cadd(b, d), t3 = csub(b, d);
+      a = cadd(t0, t2);
+      c = csub(t0, t2);
+      addsub_rot<INV>(t1, t3, b, d);
+    }
     dft4<INV>(v[12], v[13], v[14], v[15]);
     // transpose v[4 qb + qa] -> X[qb + 4 qa]
     C t;

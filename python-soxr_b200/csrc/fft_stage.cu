@@ -45,6 +45,13 @@ const char *upload_vec(const std::vector<R> &v, DevBuf *dst) {
 
 bool is_pow2i(int x) { return x > 0 && !(x & (x - 1)); }
 
+size_t tab_bytes(const FftStageInfo &fi, size_t real_size);
+size_t smem_for(const FftStageInfo &fi, size_t real_size, int groups);
+int groups_for(const FftStageInfo &fi, bool is_double) {
+  const int T = fi.n / 16;
+  return is_double ? 1 : (T >= 256 ? 1 : 256 / T);   // == FftCta<R, LOG2N>::G
+}
+
 template <typename R>
 const char *prepare_t(DevicePlan *dp, FftStageInfo &fi) {
   const Stage &st = dp->plan.stages[fi.stage_index];
@@ -99,9 +106,10 @@ const char *prepare_t(DevicePlan *dp, FftStageInfo &fi) {
   if (fi.fused_poly) {
     const Stage &ps = dp->plan.stages[fi.stage_index + 1];
     DevStage &pd = dp->stages[fi.stage_index + 1];
-    std::vector<R> tab((size_t(fi.pL) * fi.nrow * sizeof(R) + 15) / 16 * 16 / sizeof(R), R(0));
+    // rows: [pE zeros][nc taps][zeros up to nrow]; a trailing all-zero row absorbs shifted over-reads
+    std::vector<R> tab(tab_bytes(fi, sizeof(R)) / sizeof(R), R(0));
     for (int ph = 0; ph < fi.pL; ++ph)
-      for (int k = 0; k < fi.nc; ++k) tab[size_t(ph) * fi.nrow + k] = R(ps.table[size_t(ph) * fi.nc + k]);
+      for (int k = 0; k < fi.nc; ++k) tab[size_t(ph) * fi.nrow + fi.pE + k] = R(ps.table[size_t(ph) * fi.nc + k]);
     if ((e = upload_vec(tab, &pd.ptab))) return e;
   }
   return nullptr;
@@ -110,23 +118,25 @@ const char *prepare_t(DevicePlan *dp, FftStageInfo &fi) {
 template <typename R, int LOG2N, int L, int M, bool POLY>
 const char *launch(const FftStageInfo &fi, const FftKParams &P, long long n_items, cudaStream_t st) {
   auto kern = k_fft_stage<R, LOG2N, L, M, POLY>;
-  static bool attr_done[8] = {false, false, false, false, false, false, false, false};
+  static size_t attr_smem[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 8 && !attr_done[dev]) {
-    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_done[dev] = true;
+  constexpr int G = FftCta<R, LOG2N>::G, THREADS = FftCta<R, LOG2N>::THREADS;
+  const size_t smem = smem_for(fi, sizeof(R), G);
+  if (dev >= 8 || attr_smem[dev] < smem) {   // opt in to > 48 kB of dynamic shared memory
+    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    if (dev < 8) attr_smem[dev] = smem;
   }
   static int sm_count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (dev < 8 && !sm_count[dev]) cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
   const int sms = dev < 8 && sm_count[dev] ? sm_count[dev] : 148;
   int per_sm = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, fi.threads, fi.smem_bytes) != cudaSuccess || per_sm < 1) {
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem) != cudaSuccess || per_sm < 1) {
     cudaGetLastError();
     per_sm = 1;
   }
-  const long long grid = std::min<long long>(n_items, (long long)sms * per_sm);
-  kern<<<unsigned(grid), fi.threads, fi.smem_bytes, st>>>(P);
+  const long long grid = std::min<long long>((n_items + G - 1) / G, (long long)sms * per_sm);
+  kern<<<unsigned(grid), THREADS, smem, st>>>(P);
   B2_COUNT_LAUNCH();
   B2_CUDA(cudaGetLastError());
   return nullptr;
@@ -153,21 +163,54 @@ const char *launch_n(const FftStageInfo &fi, const FftKParams &P, long long n_it
   return "internal: fused FFT stage built for n in [512, 4096] only";
 }
 
-// stride of one output phase inside U: room for the 4-tap chunk over-read, even, and for L == 2
-// congruent to 8 mod 16 so that the two phase planes start half a bank-wheel apart
-int u_stride(const FftStageInfo &fi) {
-  int us = (fi.v_base + fi.delta + 4 + 1) & ~1;
-  if (fi.L == 2) while ((us & 15) != 8) us += 2;
-  return us;
+size_t tab_bytes(const FftStageInfo &fi, size_t real_size) {
+  return ((size_t(fi.pL) + 1) * fi.nrow * real_size + 64 * real_size + 15) / 16 * 16;
 }
 
-size_t smem_for(const FftStageInfo &fi, size_t real_size) {
+size_t smem_for(const FftStageInfo &fi, size_t real_size, int groups) {
   const size_t csz = 2 * real_size;
   const size_t buf_elems = size_t(fi.n) + (fi.n >> 4) + (csz == 8 ? (fi.n >> 8) : (fi.n >> 7)) + 8;
-  const size_t us = size_t(u_stride(fi));
-  size_t bytes = (buf_elems + size_t(fi.L) * us) * csz;
-  if (fi.fused_poly) bytes += (size_t(fi.pL) * fi.nrow * real_size + 15) / 16 * 16;
+  size_t bytes = size_t(groups) * (buf_elems + size_t(fi.u_elems)) * csz;
+  if (fi.fused_poly) bytes += tab_bytes(fi, real_size);
   return bytes;
+}
+
+// Sliding-window variants compiled into the kernel (fft_stage.cuh): {id, RW, B, NT}.
+struct SlideVariant { int id, rw, b, nt; };
+const SlideVariant kSlide[] = {{1, 7, 2, 22}, {2, 7, 2, 16}, {3, 5, 1, 24}, {4, 6, 1, 16}, {5, 3, 2, 14}};
+
+// Largest coefficient shift e_i = floor((rem0 + i*pM)/pL) - i*B over all start phases, i < rw.
+int max_shift(int pL, int pM, int B, int rw) {
+  int mx = 0;
+  for (int rem0 = 0; rem0 < pL; ++rem0) {
+    const long long v = ((long long)rem0 + (long long)(rw - 1) * pM) / pL - (long long)(rw - 1) * B;
+    mx = std::max<long long>(mx, v);
+  }
+  return mx;
+}
+
+void choose_poly_variant(FftStageInfo *fi, bool is_double) {
+  fi->pv = 0;
+  fi->pE = 0;
+  fi->ncp = (fi->nc + 3) & ~3;          // one output per thread: taps in chunks of 4
+  fi->nrow = fi->ncp | 1;               // odd row stride: phases spread over all banks
+  if (is_double || fi->M != 1 || fi->L > 2) return;
+  if (const char *env = std::getenv("B200SOXR_NO_SLIDE"))
+    if (env[0] == '1') return;
+  const int B = fi->pM / fi->pL;
+  int best_waste = 1 << 30;
+  for (const SlideVariant &v : kSlide) {
+    if (v.b != B) continue;
+    const int E = v.nt - fi->nc;
+    if (E < 0 || E < max_shift(fi->pL, fi->pM, B, v.rw)) continue;
+    const int waste = E * 8 - v.rw;     // fewer padded taps first, then the longer run
+    if (waste < best_waste) {
+      best_waste = waste;
+      fi->pv = v.id;
+      fi->pE = E;
+      fi->nrow = (v.nt + 1) | 1;
+    }
+  }
 }
 
 }  // namespace
@@ -217,18 +260,19 @@ const char *fft_stage_prepare(DevicePlan *dp) {
       fi->p_at0 = ps.at0_int;
       fi->p_pre = ps.dev_preload;
       fi->nc = ps.num_coefs;
-      fi->ncp = (ps.num_coefs + 3) & ~3;   // rows zero-padded to whole 4-tap chunks
-      fi->nrow = fi->ncp | 1;              // odd row stride: phases spread over all banks
       fi->delta = (ps.num_coefs - 1 + L - 1) / L;
       fi->fused_poly = true;
-      const size_t need = smem_for(*fi, dp->is_double ? 8 : 4);
-      if (need > 200 * 1024 || fi->delta >= fi->span || L * fi->delta > fi->threads) {
+      choose_poly_variant(fi.get(), dp->is_double);
+      fi->u_elems = (L * (fi->delta + fi->v_base) + 64 + 1) & ~1;
+      const size_t need = smem_for(*fi, dp->is_double ? 8 : 4, groups_for(*fi, dp->is_double));
+      if (need > 220 * 1024 || fi->delta >= fi->span || L * fi->delta > fi->threads) {
         fi->fused_poly = false;
         fi->delta = 0;
       }
     }
-    fi->smem_bytes = smem_for(*fi, dp->is_double ? 8 : 4);
-    if (fi->smem_bytes > 200 * 1024) continue;
+    if (!fi->fused_poly) fi->u_elems = (L * fi->v_base + 1) & ~1;
+    fi->smem_bytes = smem_for(*fi, dp->is_double ? 8 : 4, groups_for(*fi, dp->is_double));
+    if (fi->smem_bytes > 220 * 1024) continue;
     const char *e = dp->is_double ? prepare_t<double>(dp, *fi) : prepare_t<float>(dp, *fi);
     if (e) return e;
     dp->fft = fi;
@@ -278,18 +322,18 @@ const char *fft_stage_run(const DevicePlan &dp, const FftStageInfo &fi, const Si
   P.k0 = fi.k0;
   P.v_base = fi.v_base;
   P.delta = fi.delta;
-  P.us = u_stride(fi);
+  P.u_elems = fi.u_elems;
   const size_t csz = dp.is_double ? 16 : 8;
   P.spec = ds.spec.p;
   P.tw2 = ds.twid.p;
   P.tw3 = static_cast<const char *>(ds.twid.p) + size_t(16) * (fi.n / 256) * csz;
   P.edge = ds.edge.p;
   P.ptab = nullptr;
-  P.pL = fi.pL; P.pM = fi.pM; P.p_at0 = fi.p_at0; P.p_pre = fi.p_pre; P.nc = fi.nc; P.ncp = fi.ncp; P.nrow = fi.nrow;
+  P.pL = fi.pL; P.pM = fi.pM; P.p_at0 = fi.p_at0; P.p_pre = fi.p_pre; P.nc = fi.nc; P.ncp = fi.ncp; P.nrow = fi.nrow; P.pv = fi.pv; P.pE = fi.pE;
   P.ptab_bytes = 0;
   if (fi.fused_poly) {
     P.ptab = dp.stages[fi.stage_index + 1].ptab.p;
-    P.ptab_bytes = unsigned((size_t(fi.pL) * fi.nrow * (dp.is_double ? 8 : 4) + 15) / 16 * 16);
+    P.ptab_bytes = unsigned(tab_bytes(fi, dp.is_double ? 8 : 4));
   }
   const long long n_items = (long long)P.n_pairs * P.n_blocks;
   if (dp.is_double)

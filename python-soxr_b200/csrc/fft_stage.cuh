@@ -45,7 +45,8 @@ struct FftStageInfo {
   long k0 = 0;                   // input index of point 0 (phase 0) of block 0
   int span = 0, v_base = 0;      // valid outputs per block and phase = n - span
   int delta = 0;                 // halo (base-rate samples) kept in front of a block for the poly stage
-  int pL = 1, pM = 1, p_at0 = 0, p_pre = 0, nc = 0, ncp = 0, nrow = 0;
+  int pL = 1, pM = 1, p_at0 = 0, p_pre = 0, nc = 0, ncp = 0, nrow = 0, pv = 0, pE = 0;
+  int u_elems = 0;
   size_t smem_bytes = 0;
   int threads = 0;
   int max_ctas_per_sm = 1;
@@ -59,9 +60,11 @@ struct FftKParams {
   int n_blocks;
   long o0, o1;
   long k0;
-  int v_base, delta, us;         // us: stride of one output phase inside U
+  int v_base, delta;
+  int u_elems;                   // complex elements of U incl. zeroed slack; U[(delta + i) * L + r]
   const void *spec, *tw2, *tw3, *edge, *ptab;
   int pL, pM, p_at0, p_pre, nc, ncp, nrow;   // ncp: taps looped (multiple of 4); nrow: odd row stride
+  int pv, pE;                    // sliding-window variant id (0: one output per thread) and its lead zeros
   unsigned ptab_bytes;
 };
 
@@ -177,14 +180,25 @@ template <int BYTES> __host__ __device__ constexpr int physc(int p) {
 }
 
 // ---------------------------------------------------------------------------
-// K3 out of shared memory: outputs [n_lo, n_hi) of one block, one output per
-// thread per trip.  U holds the block's FFT-stage output (planar by phase r).
-// The tap loop runs in chunks of 4 (table rows are zero-padded to ncp = 4*nq).
+// K3 out of shared memory.  U holds the block's FFT-stage output in output-rate
+// order (element j - ubase).  Table rows: [pE zeros][nc taps][zeros], stride nrow.
+// Results go to `ostage` (shared) when `staged`, else straight to the caller.
 // ---------------------------------------------------------------------------
-template <typename R, int L, int T>
+template <typename R>
+struct OutPair {
+  const SigDesc *d;
+  long long off0, off1;
+  bool has1, vec;
+  __device__ __forceinline__ void put(long n, typename V2<R>::type v) const {
+    store_pair<R>(*d, off0, off1, has1, vec, n, v);
+  }
+};
+
+// one output per thread per trip; taps in chunks of 4 (rows zero-padded to ncp)
+template <typename R, int T>
 __device__ __forceinline__ void poly_emit(const FftKParams &P, const typename V2<R>::type *__restrict__ U,
-                                          const R *__restrict__ tab, long n_lo, long n_hi, long ubase, int t,
-                                          long long ooff0, long long ooff1, bool has1, bool ovec) {
+                                          const R *__restrict__ tab, typename V2<R>::type *__restrict__ ostage,
+                                          bool staged, long n_lo, long n_hi, long ubase, int t, const OutPair<R> &op) {
   typedef typename V2<R>::type C;
   if (n_lo + t >= n_hi) return;
   const long long at = (long long)P.p_at0 + (long long)(n_lo + t) * P.pM;
@@ -193,47 +207,69 @@ __device__ __forceinline__ void poly_emit(const FftKParams &P, const typename V2
   const int dstep = int((long long)T * P.pM / P.pL), rstep = int((long long)T * P.pM % P.pL);
   const int nq = P.ncp >> 2;
   for (long nn = n_lo + t; nn < n_hi; nn += T) {
-    const int rel = int(div - P.p_pre - ubase);
-    const R *__restrict__ c = tab + rem * P.nrow;
-    R ax = R(0), ay = R(0);
-    if (L == 1) {
-      const C *__restrict__ A = U + rel;
-#pragma unroll 2
-      for (int q = 0; q < nq; ++q) {
-        const R c0 = c[4 * q], c1 = c[4 * q + 1], c2 = c[4 * q + 2], c3 = c[4 * q + 3];
-        const C u0 = A[4 * q], u1 = A[4 * q + 1], u2 = A[4 * q + 2], u3 = A[4 * q + 3];
-        ax = fma(c0, u0.x, ax); ay = fma(c0, u0.y, ay);
-        ax = fma(c1, u1.x, ax); ay = fma(c1, u1.y, ay);
-        ax = fma(c2, u2.x, ax); ay = fma(c2, u2.y, ay);
-        ax = fma(c3, u3.x, ax); ay = fma(c3, u3.y, ay);
-      }
-    } else if (L == 2) {
-      // tap k reads U index rel + k: even taps from plane (rel & 1), odd taps from the other one
-      const int par = rel & 1, h = rel >> 1;
-      const C *__restrict__ A = U + par * P.us + h;
-      const C *__restrict__ B = U + (1 - par) * P.us + h + par;
-#pragma unroll 2
-      for (int q = 0; q < nq; ++q) {
-        const R c0 = c[4 * q], c1 = c[4 * q + 1], c2 = c[4 * q + 2], c3 = c[4 * q + 3];
-        const C u0 = A[2 * q], u1 = B[2 * q], u2 = A[2 * q + 1], u3 = B[2 * q + 1];
-        ax = fma(c0, u0.x, ax); ay = fma(c0, u0.y, ay);
-        ax = fma(c1, u1.x, ax); ay = fma(c1, u1.y, ay);
-        ax = fma(c2, u2.x, ax); ay = fma(c2, u2.y, ay);
-        ax = fma(c3, u3.x, ax); ay = fma(c3, u3.y, ay);
-      }
-    } else {
-      for (int k = 0; k < P.nc; ++k) {
-        const int idx = rel + k;
-        const C u = U[(idx % L) * P.us + idx / L];
-        const R cv = c[k];
-        ax = fma(cv, u.x, ax);
-        ay = fma(cv, u.y, ay);
-      }
-    }
+    const C *__restrict__ A = U + int(div - P.p_pre - ubase);
+    const R *__restrict__ c = tab + rem * P.nrow + P.pE;
     C o;
-    o.x = ax;
-    o.y = ay;
-    store_pair<R>(P.out, ooff0, ooff1, has1, ovec, nn, o);
+    o.x = R(0);
+    o.y = R(0);
+#pragma unroll 2
+    for (int q = 0; q < nq; ++q) {
+      const R c0 = c[4 * q], c1 = c[4 * q + 1], c2 = c[4 * q + 2], c3 = c[4 * q + 3];
+      const C u0 = A[4 * q], u1 = A[4 * q + 1], u2 = A[4 * q + 2], u3 = A[4 * q + 3];
+      o = axpy(c0, u0, o);
+      o = axpy(c1, u1, o);
+      o = axpy(c2, u2, o);
+      o = axpy(c3, u3, o);
+    }
+    if (staged) ostage[nn - n_lo] = o;
+    else op.put(nn, o);
+    div += dstep;
+    rem += rstep;
+    if (rem >= P.pL) { rem -= P.pL; ++div; }
+  }
+}
+
+// Sliding window: a thread computes RW consecutive outputs from one register-resident run of
+// (RW-1)*B + NT samples.  Output i's window starts at w_0 + i*B + e_i with 0 <= e_i <= pE; the
+// e_i shift is applied to the COEFFICIENT address (rows carry pE leading zeros), so sample
+// registers are indexed statically.  Cuts shared-memory bytes per output ~2x and makes the lane
+// strides of both access patterns odd (scratch/poly_bank_sim.py).
+template <typename R, int T, int RW, int B, int NT>
+__device__ __forceinline__ void poly_emit_slide(const FftKParams &P, const typename V2<R>::type *__restrict__ U,
+                                                const R *__restrict__ tab, typename V2<R>::type *__restrict__ ostage,
+                                                bool staged, long n_lo, long n_hi, long ubase, int t,
+                                                const OutPair<R> &op) {
+  typedef typename V2<R>::type C;
+  const long ngroups = (n_hi - n_lo + RW - 1) / RW;
+  if (t >= ngroups) return;
+  const long long at = (long long)P.p_at0 + (long long)(n_lo + (long)t * RW) * P.pM;
+  long div = long(at / P.pL);
+  int rem = int(at % P.pL);
+  const long long gs = (long long)T * RW * P.pM;
+  const int dstep = int(gs / P.pL), rstep = int(gs % P.pL);
+  const int fr = P.pM - B * P.pL;   // 0 <= fr < pL
+  for (long g = t; g < ngroups; g += T) {
+    const C *__restrict__ A = U + int(div - P.p_pre - ubase);
+    C s[(RW - 1) * B + NT];
+#pragma unroll
+    for (int m = 0; m < (RW - 1) * B + NT; ++m) s[m] = A[m];
+    const long n0 = n_lo + g * RW;
+    int ri = rem, sh = P.pE;
+#pragma unroll
+    for (int i = 0; i < RW; ++i) {
+      const R *__restrict__ c = tab + ri * P.nrow + sh;
+      C o;
+      o.x = R(0);
+      o.y = R(0);
+#pragma unroll
+      for (int k = 0; k < NT; ++k) o = axpy(c[k], s[i * B + k], o);
+      if (n0 + i < n_hi) {
+        if (staged) ostage[n0 + i - n_lo] = o;
+        else op.put(n0 + i, o);
+      }
+      ri += fr;
+      if (ri >= P.pL) { ri -= P.pL; --sh; }
+    }
     div += dstep;
     rem += rstep;
     if (rem >= P.pL) { rem -= P.pL; ++div; }
@@ -244,43 +280,57 @@ __device__ __forceinline__ void poly_emit(const FftKParams &P, const typename V2
 // The kernel.  R: engine real type.  n = 2^LOG2N.  L, M: stage ratio.  POLY: a
 // rational polyphase stage (vpoly0) consumes the block from shared memory.
 // ---------------------------------------------------------------------------
+// Threads per CTA: G independent groups of T = n/16 threads (own exchange buffer and U, named
+// barriers) share one coefficient table, so that more warps fit next to it on an SM.
+template <typename R, int LOG2N> struct FftCta {
+  static constexpr int T = (1 << LOG2N) / 16;
+  static constexpr int G = sizeof(R) == 4 ? (T >= 256 ? 1 : 256 / T) : 1;
+  static constexpr int THREADS = T * G;
+  static constexpr int MIN_CTAS = sizeof(R) == 4 ? 2 : 1;   // f32: <= 128 registers per thread
+};
+
+template <int G, int T> __device__ __forceinline__ void group_sync(int grp) {
+  if (G == 1) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(T) : "memory");
+}
+
 template <typename R, int LOG2N, int L, int M, bool POLY>
-__global__ void __launch_bounds__((1 << LOG2N) / 16) k_fft_stage(const FftKParams P) {
+__global__ void __launch_bounds__(FftCta<R, LOG2N>::THREADS, FftCta<R, LOG2N>::MIN_CTAS) k_fft_stage(const FftKParams P) {
   typedef typename V2<R>::type C;
-  constexpr int N = 1 << LOG2N, R1 = N / 256, T = N / 16, NB1 = 16 / R1;
+  constexpr int N = 1 << LOG2N, R1 = N / 256, T = N / 16, NB1 = 16 / R1, G = FftCta<R, LOG2N>::G;
   constexpr int EB = int(sizeof(C));
   constexpr int BUF_ELEMS = N + (N >> 4) + (EB == 8 ? (N >> 8) : (N >> 7)) + 8;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  C *buf = reinterpret_cast<C *>(smem_raw);
+  const int grp = G == 1 ? 0 : int(threadIdx.x) / T;
+  const int t = G == 1 ? int(threadIdx.x) : int(threadIdx.x) % T;
+  C *buf = reinterpret_cast<C *>(smem_raw) + size_t(grp) * (BUF_ELEMS + P.u_elems);
   C *U = buf + BUF_ELEMS;
-  R *tab = reinterpret_cast<R *>(U + size_t(L) * P.us);
+  R *tab = reinterpret_cast<R *>(reinterpret_cast<C *>(smem_raw) + size_t(G) * (BUF_ELEMS + P.u_elems));
   __shared__ __align__(8) unsigned long long tab_bar;
 
-  const int t = threadIdx.x;
   const C *__restrict__ tw2 = static_cast<const C *>(P.tw2);
   const C *__restrict__ tw3 = static_cast<const C *>(P.tw3) + t;
   const C *__restrict__ spec = static_cast<const C *>(P.spec) + t;
 
   if (POLY) {   // K8's table: staged once per CTA with a TMA bulk copy, waited for before the first use
-    if (t == 0) {
+    if (threadIdx.x == 0) {
       mbar_init(&tab_bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (t == 0) {
+    if (threadIdx.x == 0) {
       mbar_expect_tx(&tab_bar, P.ptab_bytes);
       tma_bulk_g2s(tab, P.ptab, P.ptab_bytes, &tab_bar);
     }
   }
   bool tab_ready = !POLY;
-  if (POLY) {   // slack behind each phase plane: over-read by the last 4-tap chunk with zero coefficients
-    const int pad0 = P.delta + P.v_base, npad = P.us - pad0;
-    for (int i = t; i < L * npad; i += T) {
+  if (POLY) {   // slack behind the block: over-read (with zero coefficients) by the polyphase stage
+    for (int i = L * (P.delta + P.v_base) + t; i < P.u_elems; i += T) {
       C z;
       z.x = R(0);
       z.y = R(0);
-      U[(i / npad) * P.us + pad0 + i % npad] = z;
+      U[i] = z;
     }
   }
 
@@ -299,7 +349,7 @@ __global__ void __launch_bounds__((1 << LOG2N) / 16) k_fft_stage(const FftKParam
   const long LV = long(L) * P.v_base;
   const long long n_items = (long long)P.n_pairs * P.n_blocks;
 
-  for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+  for (long long item = (long long)blockIdx.x * G + grp; item < n_items; item += (long long)gridDim.x * G) {
     const unsigned pair = unsigned(item / P.n_blocks);
     const long b = P.b_first + long(item % P.n_blocks);
     // signal 2cp of clip `clip` in the real part, 2cp+1 (if the clip has it) in the imaginary part
@@ -351,7 +401,7 @@ __global__ void __launch_bounds__((1 << LOG2N) / 16) k_fft_stage(const FftKParam
 #pragma unroll
           for (int m1 = 0; m1 < R1; ++m1) v[u * R1 + m1] = pin.load(k0 + long(M) * (t + T * u + 256 * m1) + s);
       }
-      __syncthreads();   // buf (and U) free: previous item / phase finished reading
+      group_sync<G, T>(grp);   // buf (and U) free: previous item / phase finished reading
 #pragma unroll
       for (int u = 0; u < NB1; ++u) {
         C a[R1];
@@ -361,7 +411,7 @@ __global__ void __launch_bounds__((1 << LOG2N) / 16) k_fft_stage(const FftKParam
 #pragma unroll
         for (int q1 = 0; q1 < R1; ++q1) b1p[u][q1] = a[q1];
       }
-      __syncthreads();
+      group_sync<G, T>(grp);
 #pragma unroll
       for (int m = 0; m < 16; ++m) v[m] = b2p[physc<EB>(R1 * m)];
 #pragma unroll
@@ -369,7 +419,7 @@ __global__ void __launch_bounds__((1 << LOG2N) / 16) k_fft_stage(const FftKParam
       Dft<16>::template run<false>(v);
 #pragma unroll
       for (int q = 0; q < 16; ++q) b2p[physc<EB>(R1 * q)] = v[q];
-      __syncthreads();
+      group_sync<G, T>(grp);
 #pragma unroll
       for (int m = 0; m < 16; ++m) v[m] = b3p[physc<EB>(T * m)];
 #pragma unroll
@@ -388,19 +438,17 @@ __global__ void __launch_bounds__((1 << LOG2N) / 16) k_fft_stage(const FftKParam
         C acc = cmul(Z[0][q], spec[((r * M + 0) * 16 + q) * T]);
 #pragma unroll
         for (int s = 1; s < M; ++s) {
-          const C e = cmul(Z[s][q], spec[((r * M + s) * 16 + q) * T]);
-          acc.x += e.x;
-          acc.y += e.y;
+          acc = cadd(acc, cmul(Z[s][q], spec[((r * M + s) * 16 + q) * T]));
         }
         v[q] = acc;
       }
       Dft<16>::template run<true>(v);
 #pragma unroll
       for (int m = 1; m < 16; ++m) v[m] = cmulc(v[m], tw3[m * T]);
-      __syncthreads();   // previous readers of buf are done
+      group_sync<G, T>(grp);   // previous readers of buf are done
 #pragma unroll
       for (int m = 0; m < 16; ++m) b3p[physc<EB>(T * m)] = v[m];
-      __syncthreads();
+      group_sync<G, T>(grp);
 #pragma unroll
       for (int q = 0; q < 16; ++q) v[q] = b2p[physc<EB>(R1 * q)];
       Dft<16>::template run<true>(v);
@@ -408,8 +456,8 @@ __global__ void __launch_bounds__((1 << LOG2N) / 16) k_fft_stage(const FftKParam
       for (int m = 1; m < 16; ++m) v[m] = cmulc(v[m], tw2[m * R1]);
 #pragma unroll
       for (int m = 0; m < 16; ++m) b2p[physc<EB>(R1 * m)] = v[m];
-      __syncthreads();
-      C *const Ur = U + r * P.us + P.delta;
+      group_sync<G, T>(grp);
+      C *const Ur = U + P.delta * L + r;
 #pragma unroll
       for (int u = 0; u < NB1; ++u) {
         C a[R1];
@@ -420,12 +468,12 @@ __global__ void __launch_bounds__((1 << LOG2N) / 16) k_fft_stage(const FftKParam
 #pragma unroll
         for (int m1 = 0; m1 < R1; ++m1) {
           const int i = g + 256 * m1;            // block-local output index i'
-          if (i < P.v_base) Ur[i] = a[m1];
-          else if (POLY && i >= N - P.delta) Ur[i - N] = a[m1];   // circular tail = halo (uncorrected)
+          if (i < P.v_base) Ur[i * L] = a[m1];
+          else if (POLY && i >= N - P.delta) Ur[(i - N) * L] = a[m1];   // circular tail = halo (uncorrected)
         }
       }
     }
-    __syncthreads();
+    group_sync<G, T>(grp);
 
     const long J0 = b * LV;   // first valid output of this block (output-rate index of the FFT stage)
     const long long ooff0 = (long long)(s0 / P.out.channels) * P.out.clip_stride +
@@ -439,29 +487,48 @@ __global__ void __launch_bounds__((1 << LOG2N) / 16) k_fft_stage(const FftKParam
       // halo: add the wrap-around correction; the intermediate does not exist before index 0 (cr.c:487-490)
       if (t < L * P.delta) {
         const int r = t / P.delta, hi = t % P.delta;
-        C h = U[r * P.us + hi];
+        C h = U[hi * L + r];
         h.x += corr.x;
         h.y += corr.y;
         if (b == 0) { h.x = R(0); h.y = R(0); }
-        U[r * P.us + hi] = h;
+        U[hi * L + r] = h;
       }
       if (!tab_ready) {
         mbar_wait(&tab_bar, 0);
         tab_ready = true;
       }
-      __syncthreads();
+      group_sync<G, T>(grp);
       const long long Q0 = (long long)J0 - P.nc + 1 + P.p_pre, Q1 = Q0 + LV;
       long n_lo = b == 0 ? 0 : long(max(0LL, ceil_div_ll(Q0 * P.pL - P.p_at0, P.pM)));
       long n_hi = long(max(0LL, ceil_div_ll(Q1 * P.pL - P.p_at0, P.pM)));
       n_lo = max(n_lo, P.o0);
       n_hi = min(n_hi, P.o1);
-      poly_emit<R, L, T>(P, U, tab, n_lo, n_hi, J0 - long(L) * P.delta, t, ooff0, ooff1, has1, ovec);
+      const OutPair<R> op{&P.out, ooff0, ooff1, has1, ovec};
+      const long ubase = J0 - long(L) * P.delta;
+      const bool staged = n_hi - n_lo <= BUF_ELEMS;   // buf is free now: stage results for coalesced stores
+      bool done = false;
+      if (sizeof(R) == 4 && M == 1 && L <= 2) {
+        done = true;
+        switch (P.pv) {
+          case 1: poly_emit_slide<R, T, 7, 2, 22>(P, U, tab, buf, staged, n_lo, n_hi, ubase, t, op); break;
+          case 2: poly_emit_slide<R, T, 7, 2, 16>(P, U, tab, buf, staged, n_lo, n_hi, ubase, t, op); break;
+          case 3: poly_emit_slide<R, T, 5, 1, 24>(P, U, tab, buf, staged, n_lo, n_hi, ubase, t, op); break;
+          case 4: poly_emit_slide<R, T, 6, 1, 16>(P, U, tab, buf, staged, n_lo, n_hi, ubase, t, op); break;
+          case 5: poly_emit_slide<R, T, 3, 2, 14>(P, U, tab, buf, staged, n_lo, n_hi, ubase, t, op); break;
+          default: done = false;
+        }
+      }
+      if (!done) poly_emit<R, T>(P, U, tab, buf, staged, n_lo, n_hi, ubase, t, op);
+      if (staged) {
+        group_sync<G, T>(grp);
+        for (long nn = n_lo + t; nn < n_hi; nn += T) op.put(nn, buf[nn - n_lo]);
+      }
     } else {
       // ---- emit the block: out[J0 + L i' + r], interleaving the L output phases ----
       const long lo = max(J0, P.o0), hi = min(J0 + LV, P.o1);
       for (long j = lo + t; j < hi; j += T) {
         const int idx = int(j - J0);
-        store_pair<R>(P.out, ooff0, ooff1, has1, ovec, j, U[(idx % L) * P.us + idx / L]);
+        store_pair<R>(P.out, ooff0, ooff1, has1, ovec, j, U[idx]);
       }
     }
   }
