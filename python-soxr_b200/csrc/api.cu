@@ -480,80 +480,138 @@ b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *d, void co
     return size_t((l.n_clips - 1) * l.clip_stride + (long long)(frames - 1) * l.frame_stride +
                   (l.channels - 1) * l.chan_stride + 1);
   };
-  const void *dev_in = in;
-  void *dev_out = out;
   const size_t in_span = span(li, d->ilen), out_span = span(lo, total);
-  if (!dev_ptrs) {
-    if ((e = ws->in_stage.reserve(std::max<size_t>(1, in_span) * isz))) return e;
-    if ((e = ws->out_stage.reserve(std::max<size_t>(1, out_span) * isz))) return e;
-    if (in_span) B2_CUDA(cudaMemcpyAsync(ws->in_stage.p, in, in_span * isz, cudaMemcpyHostToDevice, st));
-    if (out_span) B2_CUDA(cudaMemsetAsync(ws->out_stage.p, 0, out_span * isz, st));
-    dev_in = ws->in_stage.p;
-    dev_out = ws->out_stage.p;
+
+  // dither bookkeeping (identical for every clip: the seed walk restarts per clip)
+  DitherCfg dc;
+  const bool int_out = d->dtype > B200SOXR_FLOAT64;
+  if (int_out && total) {
+    dc.enabled = d->dtype == B200SOXR_INT16 && !(d->flags & B200SOXR_BATCH_NO_DITHER);
+    dc.split = d->flags & B200SOXR_BATCH_SPLIT_SEMANTICS;
+    unsigned long long bits;
+    std::memcpy(&bits, &io_ratio, 8);
+    dc.seed0 = d->channels ^ bits;                                 // soxr.c:439
+    if (dc.enabled) {
+      CallEmu emu(dp->plan);
+      const size_t cap = size_t(double(d->ilen) * d->out_rate / d->in_rate + 1);   // soxr_ext.cpp:238
+      size_t pos = 0;
+      if (d->flags & B200SOXR_BATCH_EMULATE_CALLS) {
+        const size_t dl = div_len_of(d->in_rate, d->out_rate);
+        for (size_t idx = 0; idx < d->ilen; idx += dl) {
+          const size_t od = emu.process(std::min(dl, d->ilen - idx), cap - pos);
+          dc.call_lens.push_back((long long)od);
+          pos += od;
+        }
+        const size_t od = emu.flush(cap - pos);
+        dc.call_lens.push_back((long long)od);
+        pos += od;
+      } else if (d->flags & B200SOXR_BATCH_ONESHOT_CALLS) {
+        emu.add_input(d->ilen);
+        const size_t od = emu.pull(cap, true);
+        dc.call_lens.push_back((long long)od);
+        pos += od;
+      } else {
+        dc.call_lens.push_back((long long)total);
+        pos = total;
+      }
+      if (pos != total) return "internal: emulated call partition does not cover the output";
+    }
+    if ((e = ws->misc.reserve(8))) return e;
+    B2_CUDA(cudaMemsetAsync(ws->misc.p, 0, 8, st));
   }
-  if (total) {
-    // the first / last launches read and write the caller's layout directly (K1 / float K7 fused)
+
+  // Compute clips [c0, c0 + nc) from device buffers laid out like the caller's.
+  // The first / last launches read and write the caller's layout directly (K1 / float K7 fused).
+  auto compute = [&](unsigned c0, unsigned nc, const void *din, void *dout) -> const char * {
     SigDesc xin;
-    xin.p = const_cast<void *>(dev_in); xin.dtype = d->dtype; xin.channels = d->channels;
+    xin.p = static_cast<char *>(const_cast<void *>(din)) + (long long)c0 * d->in_clip_stride * (long long)isz;
+    xin.dtype = d->dtype; xin.channels = d->channels;
     xin.clip_stride = d->in_clip_stride; xin.frame_stride = d->in_frame_stride; xin.chan_stride = d->in_chan_stride;
     xin.base = 0; xin.vlo = 0; xin.vhi = long(d->ilen);
-    if (d->dtype <= B200SOXR_FLOAT64) {
+    void *po = static_cast<char *>(dout) + (long long)c0 * d->out_clip_stride * (long long)isz;
+    const unsigned ns = nc * d->channels;
+    if (!int_out) {
       SigDesc od;
-      od.p = dev_out; od.dtype = d->dtype; od.channels = d->channels;
+      od.p = po; od.dtype = d->dtype; od.channels = d->channels;
       od.clip_stride = d->out_clip_stride; od.frame_stride = d->out_frame_stride; od.chan_stride = d->out_chan_stride;
       od.base = 0;
-      if ((e = run_range(*dp, xin, long(d->ilen), n_sig, d->channels, 0, long(total), od, ws, st))) return e;
-    } else {
-      const size_t ys = (total + 63) & ~size_t(63);
-      if ((e = ws->y.reserve(ys * n_sig * esz))) return e;
-      const SigDesc yd = planar_desc(ws->y.p, dp->is_double, ys, 0, 0, 0);
-      if ((e = run_range(*dp, xin, long(d->ilen), n_sig, d->channels, 0, long(total), yd, ws, st))) return e;
+      return run_range(*dp, xin, long(d->ilen), ns, d->channels, 0, long(total), od, ws, st);
+    }
+    const size_t ys = (total + 63) & ~size_t(63);
+    if (const char *e2 = ws->y.reserve(ys * ns * esz)) return e2;
+    const SigDesc yd = planar_desc(ws->y.p, dp->is_double, ys, 0, 0, 0);
+    if (const char *e2 = run_range(*dp, xin, long(d->ilen), ns, d->channels, 0, long(total), yd, ws, st)) return e2;
+    IoLayout lc = lo;
+    lc.n_clips = nc;
+    return convert_out(lc, po, 0, total, dp->is_double, ws->y.p, ys, dc, ws->misc.as<unsigned long long>(), ws, st);
+  };
 
-      DitherCfg dc;
-      dc.enabled = d->dtype == B200SOXR_INT16 && !(d->flags & B200SOXR_BATCH_NO_DITHER);
-      dc.split = d->flags & B200SOXR_BATCH_SPLIT_SEMANTICS;
-      unsigned long long bits;
-      std::memcpy(&bits, &io_ratio, 8);
-      dc.seed0 = d->channels ^ bits;                                 // soxr.c:439
-      if (dc.enabled) {
-        CallEmu emu(dp->plan);
-        const size_t cap = size_t(double(d->ilen) * d->out_rate / d->in_rate + 1);   // soxr_ext.cpp:238
-        size_t pos = 0;
-        if (d->flags & B200SOXR_BATCH_EMULATE_CALLS) {
-          const size_t dl = div_len_of(d->in_rate, d->out_rate);
-          for (size_t idx = 0; idx < d->ilen; idx += dl) {
-            const size_t od = emu.process(std::min(dl, d->ilen - idx), cap - pos);
-            dc.call_lens.push_back((long long)od);
-            pos += od;
-          }
-          const size_t od = emu.flush(cap - pos);
-          dc.call_lens.push_back((long long)od);
-          pos += od;
-        } else if (d->flags & B200SOXR_BATCH_ONESHOT_CALLS) {
-          emu.add_input(d->ilen);
-          const size_t od = emu.pull(cap, true);
-          dc.call_lens.push_back((long long)od);
-          pos += od;
-        } else {
-          dc.call_lens.push_back((long long)total);
-          pos = total;
+  if (dev_ptrs) {
+    if (total && (e = compute(0, d->n_clips, in, out))) return e;
+  } else {
+    // Host buffers: clips are cut into chunks that flow  H2D -> compute -> D2H  on three streams, so the
+    // two copy directions (one DMA engine each) and the kernels overlap; a chunk is whole clips because
+    // clips are the independent unit (soxr_ext.cpp:230: one soxr_t per clip).
+    if ((e = ws->in_stage.reserve(std::max<size_t>(1, in_span) * isz))) return e;
+    if ((e = ws->out_stage.reserve(std::max<size_t>(1, out_span) * isz))) return e;
+    const bool clip_major =
+        d->n_clips > 1 && size_t(d->in_clip_stride) >= span(IoLayout{d->dtype, 1, d->channels, 0, d->in_frame_stride, d->in_chan_stride}, d->ilen) &&
+        size_t(d->out_clip_stride) >= span(IoLayout{d->dtype, 1, d->channels, 0, d->out_frame_stride, d->out_chan_stride}, total) &&
+        d->in_clip_stride > 0 && d->out_clip_stride > 0;
+    unsigned per_chunk = d->n_clips;
+    if (clip_major && total) {
+      static const size_t kChunkBytes = [] {
+        const char *v = std::getenv("B200SOXR_CHUNK_MB");
+        const long mb = v ? std::atol(v) : 16;
+        return size_t(mb > 0 ? mb : 16) << 20;
+      }();
+      const size_t clip_bytes = std::max<size_t>(1, size_t(d->in_clip_stride) * isz);
+      per_chunk = unsigned(std::max<size_t>(1, kChunkBytes / clip_bytes));
+      per_chunk = std::max(per_chunk, (d->n_clips + 63) / 64);   // at most 64 chunks
+      per_chunk = std::min(per_chunk, d->n_clips);
+    }
+    const unsigned n_chunks = (d->n_clips + per_chunk - 1) / per_chunk;
+    if (n_chunks <= 1) {
+      if (in_span) B2_CUDA(cudaMemcpyAsync(ws->in_stage.p, in, in_span * isz, cudaMemcpyHostToDevice, st));
+      if (out_span) B2_CUDA(cudaMemsetAsync(ws->out_stage.p, 0, out_span * isz, st));
+      if (total && (e = compute(0, d->n_clips, ws->in_stage.p, ws->out_stage.p))) return e;
+      if (out_span) B2_CUDA(cudaMemcpyAsync(out, ws->out_stage.p, out_span * isz, cudaMemcpyDeviceToHost, st));
+    } else {
+      if ((e = ws->need_events(2 * size_t(n_chunks) + 1))) return e;
+      cudaEvent_t ev_start = ws->events[2 * n_chunks];
+      B2_CUDA(cudaEventRecord(ev_start, st));          // order after earlier work queued on st
+      B2_CUDA(cudaStreamWaitEvent(ws->h2d_stream, ev_start, 0));
+      B2_CUDA(cudaStreamWaitEvent(ws->d2h_stream, ev_start, 0));
+      for (unsigned c = 0; c < n_chunks; ++c) {
+        const unsigned c0 = c * per_chunk, nc = std::min(per_chunk, d->n_clips - c0);
+        IoLayout l1 = li, l2 = lo;
+        l1.n_clips = l2.n_clips = nc;
+        const size_t ispan = span(l1, d->ilen), ospan = span(l2, total);
+        const size_t ioff = size_t(c0) * size_t(d->in_clip_stride) * isz, ooff = size_t(c0) * size_t(d->out_clip_stride) * isz;
+        B2_CUDA(cudaMemcpyAsync(static_cast<char *>(ws->in_stage.p) + ioff, static_cast<const char *>(in) + ioff,
+                                ispan * isz, cudaMemcpyHostToDevice, ws->h2d_stream));
+        B2_CUDA(cudaEventRecord(ws->events[2 * c], ws->h2d_stream));
+        B2_CUDA(cudaStreamWaitEvent(st, ws->events[2 * c], 0));
+        B2_CUDA(cudaMemsetAsync(static_cast<char *>(ws->out_stage.p) + ooff, 0, ospan * isz, st));
+        if ((e = compute(c0, nc, ws->in_stage.p, ws->out_stage.p))) {
+          cudaStreamSynchronize(ws->h2d_stream); cudaStreamSynchronize(st); cudaStreamSynchronize(ws->d2h_stream);
+          return e;
         }
-        if (pos != total) return "internal: emulated call partition does not cover the output";
+        B2_CUDA(cudaEventRecord(ws->events[2 * c + 1], st));
+        B2_CUDA(cudaStreamWaitEvent(ws->d2h_stream, ws->events[2 * c + 1], 0));
+        B2_CUDA(cudaMemcpyAsync(static_cast<char *>(out) + ooff, static_cast<char *>(ws->out_stage.p) + ooff, ospan * isz,
+                                cudaMemcpyDeviceToHost, ws->d2h_stream));
       }
-      if ((e = ws->misc.reserve(8))) return e;
-      B2_CUDA(cudaMemsetAsync(ws->misc.p, 0, 8, st));
-      if ((e = convert_out(lo, dev_out, 0, total, dp->is_double, ws->y.p, ys, dc, ws->misc.as<unsigned long long>(), ws, st)))
-        return e;
-      if (clips) {
-        unsigned long long c = 0;
-        B2_CUDA(cudaMemcpyAsync(&c, ws->misc.p, 8, cudaMemcpyDeviceToHost, st));
-        B2_CUDA(cudaStreamSynchronize(st));
-        *clips = size_t(c);
-      }
+      B2_CUDA(cudaStreamSynchronize(ws->d2h_stream));
     }
   }
+  if (int_out && total && clips) {
+    unsigned long long c = 0;
+    B2_CUDA(cudaMemcpyAsync(&c, ws->misc.p, 8, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    *clips = size_t(c);
+  }
   if (!dev_ptrs) {
-    if (out_span) B2_CUDA(cudaMemcpyAsync(out, dev_out, out_span * isz, cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
   } else {
     // asynchronous return is only safe when no pooled scratch buffer is still in use by queued work

@@ -166,4 +166,100 @@ template <> struct Dft<16> {
   }
 };
 
+// ---- odd radices (3, 5, 7) and prime-factor composites (12, 14, 20) -------------------
+// Needed by the single-pass frequency-domain resampler (fdr_stage.cuh), whose block sizes are
+// 160a and 147a points.  PFFFT has radix-3/5 passes too but libsoxr compiles them out
+// (pffft.c:320,424,559,808); here they are written from the DFT definition, with the
+// symmetric-pair factorisation  X_m, X_{N-m} = a_m -+ i b_m  (forward).
+template <> struct Dft<3> {
+  template <bool INV, typename C> static __host__ __device__ __forceinline__ void run(C (&v)[3]) {
+    typedef decltype(v[0].x) R;
+    const R s = R(0.86602540378443864676);
+    const C t = cadd(v[1], v[2]), d = csub(v[1], v[2]);
+    const C a = axpy(R(-0.5), t, v[0]);
+    v[0] = cadd(v[0], t);
+    v[1] = axpy(INV ? -s : s, rot(d), a);
+    v[2] = axpy(INV ? s : -s, rot(d), a);
+  }
+};
+
+template <> struct Dft<5> {
+  template <bool INV, typename C> static __host__ __device__ __forceinline__ void run(C (&v)[5]) {
+    typedef decltype(v[0].x) R;
+    const R c1 = R(0.30901699437494742410), c2 = R(-0.80901699437494742410);
+    const R s1 = R(0.95105651629515357212), s2 = R(0.58778525229247312917);
+    const C t1 = cadd(v[1], v[4]), t2 = cadd(v[2], v[3]), d1 = csub(v[1], v[4]), d2 = csub(v[2], v[3]);
+    const C a1 = axpy(c2, t2, axpy(c1, t1, v[0])), a2 = axpy(c1, t2, axpy(c2, t1, v[0]));
+    C b1 = axpy(s2, d2, scale(s1, d1)), b2 = axpy(-s1, d2, scale(s2, d1));
+    b1 = rot(b1);
+    b2 = rot(b2);
+    v[0] = cadd(v[0], cadd(t1, t2));
+    if (INV) { v[1] = csub(a1, b1); v[4] = cadd(a1, b1); v[2] = csub(a2, b2); v[3] = cadd(a2, b2); }
+    else { v[1] = cadd(a1, b1); v[4] = csub(a1, b1); v[2] = cadd(a2, b2); v[3] = csub(a2, b2); }
+  }
+};
+
+template <> struct Dft<7> {
+  template <bool INV, typename C> static __host__ __device__ __forceinline__ void run(C (&v)[7]) {
+    typedef decltype(v[0].x) R;
+    const R c1 = R(0.62348980185873353053), c2 = R(-0.22252093395631440429), c3 = R(-0.90096886790241912624);
+    const R s1 = R(0.78183148246802980871), s2 = R(0.97492791218182360702), s3 = R(0.43388373911755812048);
+    const C t1 = cadd(v[1], v[6]), t2 = cadd(v[2], v[5]), t3 = cadd(v[3], v[4]);
+    const C d1 = csub(v[1], v[6]), d2 = csub(v[2], v[5]), d3 = csub(v[3], v[4]);
+    const C a1 = axpy(c3, t3, axpy(c2, t2, axpy(c1, t1, v[0])));
+    const C a2 = axpy(c1, t3, axpy(c3, t2, axpy(c2, t1, v[0])));
+    const C a3 = axpy(c2, t3, axpy(c1, t2, axpy(c3, t1, v[0])));
+    const C b1 = rot(axpy(s3, d3, axpy(s2, d2, scale(s1, d1))));
+    const C b2 = rot(axpy(-s1, d3, axpy(-s3, d2, scale(s2, d1))));
+    const C b3 = rot(axpy(s2, d3, axpy(-s1, d2, scale(s3, d1))));
+    v[0] = cadd(cadd(v[0], t1), cadd(t2, t3));
+    if (INV) {
+      v[1] = csub(a1, b1); v[6] = cadd(a1, b1); v[2] = csub(a2, b2); v[5] = cadd(a2, b2);
+      v[3] = csub(a3, b3); v[4] = cadd(a3, b3);
+    } else {
+      v[1] = cadd(a1, b1); v[6] = csub(a1, b1); v[2] = cadd(a2, b2); v[5] = csub(a2, b2);
+      v[3] = cadd(a3, b3); v[4] = csub(a3, b3);
+    }
+  }
+};
+
+// Good-Thomas prime-factor DFT for coprime N1, N2: no twiddles between the two sub-transforms,
+// n = (N2 n1 + N1 n2) mod N in, k = CRT(k1, k2) out; all index maps are compile-time.
+constexpr int pfa_inv_mod(int a, int m) {   // a^-1 mod m (m small)
+  int r = 1;
+  for (int i = 1; i < m; ++i)
+    if ((a * i) % m == 1) r = i;
+  return r;
+}
+template <int N1, int N2> struct PfaDft {
+  static constexpr int N = N1 * N2;
+  static constexpr int E1 = N2 * pfa_inv_mod(N2 % N1, N1), E2 = N1 * pfa_inv_mod(N1 % N2, N2);
+  template <bool INV, typename C> static __host__ __device__ __forceinline__ void run(C (&v)[N1 * N2]) {
+    C a[N2][N1];
+#pragma unroll
+    for (int n2 = 0; n2 < N2; ++n2)
+#pragma unroll
+      for (int n1 = 0; n1 < N1; ++n1) a[n2][n1] = v[(N2 * n1 + N1 * n2) % N];
+#pragma unroll
+    for (int n2 = 0; n2 < N2; ++n2) Dft<N1>::template run<INV>(a[n2]);
+#pragma unroll
+    for (int k1 = 0; k1 < N1; ++k1) {
+      C b[N2];
+#pragma unroll
+      for (int n2 = 0; n2 < N2; ++n2) b[n2] = a[n2][k1];
+      Dft<N2>::template run<INV>(b);
+#pragma unroll
+      for (int k2 = 0; k2 < N2; ++k2) v[(k1 * E1 + k2 * E2) % N] = b[k2];
+    }
+  }
+};
+template <> struct Dft<6> : PfaDft<2, 3> {};
+template <> struct Dft<10> : PfaDft<2, 5> {};
+template <> struct Dft<12> : PfaDft<4, 3> {};
+template <> struct Dft<14> : PfaDft<2, 7> {};
+template <> struct Dft<15> : PfaDft<3, 5> {};
+template <> struct Dft<20> : PfaDft<4, 5> {};
+template <> struct Dft<21> : PfaDft<3, 7> {};
+template <> struct Dft<28> : PfaDft<4, 7> {};
+
 }  // namespace b2

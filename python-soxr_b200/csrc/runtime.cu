@@ -54,6 +54,20 @@ Workspace::~Workspace() {
   for (DevBuf *b : {&in_stage, &out_stage, &x, &y, &t0, &t1, &seeds, &blocks, &misc}) b->release();
   for (PinnedBuf *b : {&pin_in, &pin_out, &pin_misc}) b->release();
   if (stream) cudaStreamDestroy(stream);
+  if (h2d_stream) cudaStreamDestroy(h2d_stream);
+  if (d2h_stream) cudaStreamDestroy(d2h_stream);
+  for (cudaEvent_t e : events) cudaEventDestroy(e);
+}
+
+const char *Workspace::need_events(size_t n) {
+  if (!h2d_stream) B2_CUDA(cudaStreamCreateWithFlags(&h2d_stream, cudaStreamNonBlocking));
+  if (!d2h_stream) B2_CUDA(cudaStreamCreateWithFlags(&d2h_stream, cudaStreamNonBlocking));
+  while (events.size() < n) {
+    cudaEvent_t e;
+    B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    events.push_back(e);
+  }
+  return nullptr;
 }
 
 namespace {

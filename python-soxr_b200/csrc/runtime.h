@@ -69,6 +69,11 @@ const char *get_device_plan(double io_ratio, const QSpec &q, const RSpec &r, dou
 struct Workspace {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // host-buffer batches: copy-in / copy-out streams (one DMA engine each way) and a pool of
+  // untimed events chaining  H2D(chunk i) -> compute(chunk i) -> D2H(chunk i)
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  std::vector<cudaEvent_t> events;
+  const char *need_events(size_t n);
   DevBuf in_stage, out_stage, x, y, t0, t1, seeds, blocks, misc;
   PinnedBuf pin_in, pin_out, pin_misc;
   ~Workspace();
