@@ -35,6 +35,8 @@ IN_RATE, OUT_RATE, QUALITY = 48000, 44100, 'VHQ'
 N_CLIPS, FRAMES, CH = 1024, 48000, 2
 METRIC = "Msamples/s 48k->44.1k VHQ f32 (input samples/s)"
 WORKLOAD = "batch=1024 clips x 1s stereo float32 48000->44100 VHQ"
+KERNEL_DESC = ("k_fdr<2560->2352> (single-pass frequency-domain resampler, 1 launch per step) "
+               "+ k_fdr_head (direct form, first 5 output frames of each clip)")
 
 
 def _peaks():
@@ -285,10 +287,11 @@ def main():
                    "l2": "inputs (393 MB) + outputs (361 MB) per step exceed the 126 MB L2; no explicit flush",
                    "output_msamples_per_s": value * out_frames / FRAMES},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": _traffic(), "kernel": "k_fft_stage<float,11,2,1,true> (1 launch per step)",
+                     "traffic": _traffic(), "kernel": KERNEL_DESC,
                      "kernel_ms_avg": k_avg, "kernel_ms_min": k_ms[0], "kernel_ms_median": k_ms[len(k_ms) // 2],
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                     "note": "FMA/shared-memory bound, not HBM bound: see DESIGN.md"},
+                     "note": "kernel_ms_* = CUDA-event time of one whole step (all its launches) on the launching stream; "
+                             "shared-memory/FMA bound, not HBM bound: see DESIGN.md"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
     if not args.no_cpu_baseline and world == 1:

@@ -131,6 +131,8 @@ B200SOXR_API b200soxr_error_t b200soxr_oneshot(double input_rate, double output_
  *      flags: B200SOXR_BATCH_DEVICE_PTRS  in/out are device pointers (no copies)
  *             B200SOXR_BATCH_NO_DITHER    == io_spec.flags SOXR_NO_DITHER
  *             B200SOXR_BATCH_DOUBLE       force the f64 engine (SOXR_DOUBLE_PRECISION)
+ *             B200SOXR_BATCH_EXACT_GRID   never use the single-pass frequency-domain kernel: results are
+ *                                         bit-identical to b200soxr_process on the same input
  *             B200SOXR_BATCH_EMULATE_CALLS int16 dither: replay the div_len call
  *                                          partition of csoxr_divide_proc (soxr_ext.cpp:239-257)
  *      `cuda_stream` is a cudaStream_t.  Host pointers: NULL => a private stream of the
@@ -143,6 +145,7 @@ B200SOXR_API b200soxr_error_t b200soxr_oneshot(double input_rate, double output_
 #define B200SOXR_BATCH_EMULATE_CALLS 8u
 #define B200SOXR_BATCH_ONESHOT_CALLS 16u  /* dither partition of a single soxr_oneshot call */
 #define B200SOXR_BATCH_SPLIT_SEMANTICS 32u /* int16 dither salted per channel, as for *_S types (soxr.c:664-677) */
+#define B200SOXR_BATCH_EXACT_GRID 64u /* always use the reference's block grid (bit-identical to a stream of the same input) */
 
 typedef struct b200soxr_batch_desc {
   double in_rate, out_rate;

@@ -465,13 +465,17 @@ b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *d, void co
   const unsigned n_sig = d->n_clips * d->channels;
   const size_t esz = dp->is_double ? 8 : 4, isz = dtype_size(d->dtype);
 
-  Workspace *ws = acquire_workspace();
+  Workspace *ws = acquire_workspace(false);
   struct Rel { Workspace *w; ~Rel() { release_workspace(w); } } rel{ws};
   // device pointers: the caller's stream as given (NULL = the legacy default stream, CUDA's own
   // convention) so the call orders with the caller's work; host pointers: NULL = a private stream
   const bool dev_ptrs0 = d->flags & B200SOXR_BATCH_DEVICE_PTRS;
   cudaStream_t st = (cuda_stream || dev_ptrs0) ? static_cast<cudaStream_t>(cuda_stream) : ws->stream;
   const char *e = nullptr;
+  if (ws->busy) {   // scratch still in use by an earlier asynchronous call: order this stream after it
+    B2_CUDA(cudaStreamWaitEvent(st, ws->busy_ev, 0));
+    ws->busy = false;
+  }
 
   IoLayout li{d->dtype, d->n_clips, d->channels, d->in_clip_stride, d->in_frame_stride, d->in_chan_stride};
   IoLayout lo{d->dtype, d->n_clips, d->channels, d->out_clip_stride, d->out_frame_stride, d->out_chan_stride};
@@ -520,6 +524,7 @@ b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *d, void co
     B2_CUDA(cudaMemsetAsync(ws->misc.p, 0, 8, st));
   }
 
+  const unsigned run_flags = (d->flags & B200SOXR_BATCH_EXACT_GRID) ? 0u : unsigned(kRunAllowFdr);
   // Compute clips [c0, c0 + nc) from device buffers laid out like the caller's.
   // The first / last launches read and write the caller's layout directly (K1 / float K7 fused).
   auto compute = [&](unsigned c0, unsigned nc, const void *din, void *dout) -> const char * {
@@ -535,12 +540,12 @@ b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *d, void co
       od.p = po; od.dtype = d->dtype; od.channels = d->channels;
       od.clip_stride = d->out_clip_stride; od.frame_stride = d->out_frame_stride; od.chan_stride = d->out_chan_stride;
       od.base = 0;
-      return run_range(*dp, xin, long(d->ilen), ns, d->channels, 0, long(total), od, ws, st);
+      return run_range(*dp, xin, long(d->ilen), ns, d->channels, 0, long(total), od, ws, st, run_flags);
     }
     const size_t ys = (total + 63) & ~size_t(63);
     if (const char *e2 = ws->y.reserve(ys * ns * esz)) return e2;
     const SigDesc yd = planar_desc(ws->y.p, dp->is_double, ys, 0, 0, 0);
-    if (const char *e2 = run_range(*dp, xin, long(d->ilen), ns, d->channels, 0, long(total), yd, ws, st)) return e2;
+    if (const char *e2 = run_range(*dp, xin, long(d->ilen), ns, d->channels, 0, long(total), yd, ws, st, run_flags)) return e2;
     IoLayout lc = lo;
     lc.n_clips = nc;
     return convert_out(lc, po, 0, total, dp->is_double, ws->y.p, ys, dc, ws->misc.as<unsigned long long>(), ws, st);
@@ -614,10 +619,11 @@ b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *d, void co
   if (!dev_ptrs) {
     B2_CUDA(cudaStreamSynchronize(st));
   } else {
-    // asynchronous return is only safe when no pooled scratch buffer is still in use by queued work
-    const size_t fused_stages = dp->fft ? (dp->fft->fused_poly ? 2 : 1) : 0;
-    const bool scratch_free = d->dtype <= B200SOXR_FLOAT64 && fused_stages == dp->plan.stages.size();
-    if (!scratch_free) B2_CUDA(cudaStreamSynchronize(st));
+    // asynchronous return: float batches leave their work queued on the caller's stream; the pooled
+    // scratch they may still be using is fenced by Workspace::busy_ev for whoever takes it next
+    if (d->dtype <= B200SOXR_FLOAT64) {
+      if ((e = ws->mark_busy(st))) return e;
+    } else B2_CUDA(cudaStreamSynchronize(st));
   }
   return nullptr;
 }

@@ -1,0 +1,281 @@
+// fdr_stage.cu -- host side of the single-pass frequency-domain resampler: eligibility, the
+// cascade's zero-phase response (double precision, from the same prototype filters the planner
+// designs: cr.c:184-248 / cr.c:398-443 via plan.cpp), twiddles, launcher.
+#include "fdr_stage.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <numeric>
+
+namespace b2 {
+
+namespace {
+const double kPi = 3.14159265358979323846264338327950288;
+
+template <typename R>
+const char *upload_vec(const std::vector<R> &v, DevBuf *dst) {
+  if (const char *e = dst->reserve(std::max<size_t>(16, v.size() * sizeof(R)))) return e;
+  B2_CUDA(cudaMemcpy(dst->p, v.data(), v.size() * sizeof(R), cudaMemcpyHostToDevice));
+  return nullptr;
+}
+
+// exp(-2 pi i a / n) with exact argument reduction
+void unit_root(long long a, long long n, double *re, double *im) {
+  a %= n;
+  if (a < 0) a += n;
+  const double ang = -2 * kPi * double(a) / double(n);
+  *re = std::cos(ang);
+  *im = std::sin(ang);
+}
+
+template <class F3>
+std::vector<float> make_twiddles(int *tw3_off) {
+  std::vector<float> tw(size_t(2) * (F3::TW2_ELEMS + F3::TW3_ELEMS));
+  for (int mp = 0; mp < F3::RB; ++mp)
+    for (int j = 0; j < F3::RA; ++j) {
+      double re, im;
+      unit_root((long long)j * mp, F3::RA * F3::RB, &re, &im);
+      tw[2 * size_t(mp * F3::RA + j)] = float(re);
+      tw[2 * size_t(mp * F3::RA + j) + 1] = float(im);
+    }
+  *tw3_off = F3::TW2_ELEMS;
+  for (int m = 0; m < F3::RC; ++m)
+    for (int t = 0; t < F3::T3; ++t) {
+      double re, im;
+      unit_root((long long)t * m, F3::N, &re, &im);
+      const size_t o = size_t(F3::TW2_ELEMS) + size_t(m) * F3::T3 + t;
+      tw[2 * o] = float(re);
+      tw[2 * o + 1] = float(im);
+    }
+  return tw;
+}
+
+bool fdr_disabled() {
+  const char *env = std::getenv("B200SOXR_NO_FDR");
+  if (env && env[0] == '1') return true;
+  env = std::getenv("B200SOXR_EXACT");
+  return env && env[0] == '1';
+}
+}  // namespace
+
+std::vector<double> fdr_response(const Plan &plan, int rin, int rout, int nin, int nout, int m_in, int *n_head) {
+  std::vector<double> none;
+  const size_t S = plan.stages.size();
+  if (S < 1 || S > 2) return none;   // k_fdr_head restates a cascade of at most two stages
+  long long Lt = 1, Mt = 1;
+  for (const Stage &s : plan.stages) {
+    if (!(s.kind == kDft || s.kind == kPoly || s.kind == kHalf) || s.g.empty()) return none;
+    Lt *= s.L;
+    Mt *= s.M;
+    if (Lt > (1 << 20) || Mt > (1 << 20)) return none;
+  }
+  const long long g = std::gcd(Lt, Mt);
+  if (Lt / g != rout || Mt / g != rin) return none;
+  // global tick = 1 / Lt input samples; stage i's fine grid (its input rate * L_i) has
+  // tick_i = prod_{s<i} M_s * prod_{s>i} L_s ticks per sample
+  std::vector<long long> tick(S);
+  double half_support = 0;   // in ticks
+  for (size_t i = 0; i < S; ++i) {
+    long long t = 1;
+    for (size_t s = 0; s < i; ++s) t *= plan.stages[s].M;
+    for (size_t s = i + 1; s < S; ++s) t *= plan.stages[s].L;
+    tick[i] = t;
+    const Stage &st = plan.stages[i];
+    if (2 * st.C != long(st.g.size()) - 1) return none;   // every stage zero-phase about a tap: real response
+    half_support += double(st.C) * double(t);
+  }
+  if (half_support > double(m_in) * double(Lt)) return none;
+  const long long Pp = Lt * nin;   // block period in ticks
+  std::vector<double> H(size_t(nout), 0.0);
+  for (int F = 0; F <= (nout - 1) / 2; ++F) {
+    double prod = 1;
+    for (size_t i = 0; i < S; ++i) {
+      const Stage &st = plan.stages[i];
+      const long c = st.C;
+      double acc = st.g[size_t(c)];
+      for (long k = 1; k <= c; ++k) {
+        // cos(2 pi F k tick / Pp), argument reduced in integers
+        long long a = ((long long)F * k) % Pp;
+        a = (a * (tick[i] % Pp)) % Pp;
+        acc += (st.g[size_t(c - k)] + st.g[size_t(c + k)]) * std::cos(2 * kPi * double(a) / double(Pp));
+      }
+      prod *= acc;
+    }
+    const double h = prod / double(Pp);
+    H[size_t(F)] = h;
+    if (F) H[size_t(nout - F)] = h;
+  }
+  // outputs whose chain of windows reaches an intermediate signal before its index 0 (which the
+  // reference treats as zero, cr.c:487-490, not as the filter's run-in)
+  int head = 0;
+  for (int n = 0; n < 65536; ++n) {
+    long r = n;
+    bool ok = true;
+    for (size_t s = S; s-- > 1;) {
+      r = stage_input_first(plan.stages[s], r);
+      if (r < 0) { ok = false; break; }
+    }
+    if (ok) { head = n; break; }
+    head = n + 1;
+  }
+  if (n_head) *n_head = head;
+  return H;
+}
+
+namespace {
+// One warp per signal: u[m] = sum_k gA[CA + MA m - LA k] x[k] (lane m), then
+// out[n] = sum_{m >= 0} gB[CB + MB n - LB m] u[m] (lane n - o0) -- the reference's cascade with its
+// intermediate signal starting at index 0 (cr.c:487-490), in double accumulation like k_rational.
+__global__ void __launch_bounds__(128) k_fdr_head(const FdrHeadParams P) {
+  __shared__ float u_s[4][64];
+  const int w = int(threadIdx.x) >> 5, lane = int(threadIdx.x) & 31;
+  const unsigned s = blockIdx.x * 4u + unsigned(w);
+  if (s < P.n_sig) {
+    const long long off = (long long)(s / P.in.channels) * P.in.clip_stride + (long long)(s % P.in.channels) * P.in.chan_stride -
+                          P.in.base * P.in.frame_stride;
+    for (int m = lane; m < P.n_u; m += 32) {
+      const long top = P.CA + long(P.MA) * m;
+      long k_hi = top / P.LA;
+      const long t = top - (P.nA - 1);
+      long k_lo = t <= 0 ? 0 : (t + P.LA - 1) / P.LA;
+      if (k_lo < P.in.vlo) k_lo = P.in.vlo;
+      if (k_hi > P.in.vhi - 1) k_hi = P.in.vhi - 1;
+      double acc = 0;
+      for (long k = k_lo; k <= k_hi; ++k)
+        acc = fma(double(P.gA[top - P.LA * k]), ld_as<double>(P.in.p, P.in.dtype, off + k * P.in.frame_stride), acc);
+      u_s[w][m] = float(acc);
+    }
+  }
+  __syncwarp();
+  if (s < P.n_sig) {
+    const long n = P.o0 + lane;
+    if (n < P.o1) {
+      const long top = P.CB + long(P.MB) * n;
+      long m_hi = top / P.LB;
+      const long t = top - (P.nB - 1);
+      const long m_lo = t <= 0 ? 0 : (t + P.LB - 1) / P.LB;
+      if (m_hi > P.n_u - 1) m_hi = P.n_u - 1;
+      double acc = 0;
+      for (long m = m_lo; m <= m_hi; ++m) acc = fma(double(P.gB[top - P.LB * m]), double(u_s[w][m]), acc);
+      const long long oo = (long long)(s / P.out.channels) * P.out.clip_stride + (long long)(s % P.out.channels) * P.out.chan_stride +
+                           (n - P.out.base) * P.out.frame_stride;
+      st_as<double>(P.out.p, P.out.dtype, oo, acc);
+    }
+  }
+}
+
+template <class Cfg>
+const char *prepare_cfg(DevicePlan *dp, int variant) {
+  int n_head = 0;
+  const std::vector<double> Hd = fdr_response(dp->plan, Cfg::RIN, Cfg::ROUT, Cfg::NIN, Cfg::NOUT, Cfg::M_IN, &n_head);
+  if (Hd.empty()) return nullptr;
+  auto fi = std::make_shared<FdrInfo>();
+  fi->variant = variant;
+  fi->n_head = n_head;
+  if (n_head > 32) return nullptr;   // one lane per head output
+  if (dp->plan.stages.size() == 2) {
+    const Stage &sb = dp->plan.stages[1];
+    fi->n_u = int((sb.C + long(sb.M) * std::max(0, n_head - 1)) / sb.L) + 1;
+    if (fi->n_u > 64) return nullptr;
+  }
+  fi->adv_in = Cfg::ADV_IN; fi->adv_out = Cfg::ADV_OUT; fi->m_in = Cfg::M_IN; fi->m_out = Cfg::M_OUT;
+  fi->nin = Cfg::NIN; fi->nout = Cfg::NOUT;
+  fi->smem_bytes = size_t(Cfg::BUF_A + Cfg::BUF_B) * sizeof(float2);
+  std::vector<float> Hf(Hd.size());
+  for (size_t i = 0; i < Hd.size(); ++i) Hf[i] = float(Hd[i]);
+  if (const char *e = upload_vec(Hf, &fi->H)) return e;
+  if (const char *e = upload_vec(make_twiddles<typename Cfg::FW>(&fi->ftw3_off), &fi->ftw)) return e;
+  if (const char *e = upload_vec(make_twiddles<typename Cfg::IV>(&fi->itw3_off), &fi->itw)) return e;
+  dp->fdr = fi;
+  return nullptr;
+}
+
+template <class Cfg>
+const char *launch_cfg(const FdrInfo &fi, const FdrKParams &P, long long n_items, cudaStream_t st) {
+  auto kern = k_fdr<Cfg>;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static bool attr_set[16] = {};
+  static int per_sm[16] = {};
+  static int sm_count[16] = {};
+  const int di = dev & 15;
+  if (!attr_set[di]) {
+    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fi.smem_bytes)));
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[di], kern, Cfg::THREADS, fi.smem_bytes) != cudaSuccess ||
+        per_sm[di] < 1) {
+      cudaGetLastError();
+      per_sm[di] = 1;
+    }
+    if (cudaDeviceGetAttribute(&sm_count[di], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count[di] < 1)
+      sm_count[di] = 148;
+    attr_set[di] = true;
+  }
+  const long long grid = std::min<long long>(n_items, (long long)sm_count[di] * per_sm[di]);
+  kern<<<unsigned(grid), Cfg::THREADS, fi.smem_bytes, st>>>(P);
+  B2_COUNT_LAUNCH();
+  B2_CUDA(cudaGetLastError());
+  return nullptr;
+}
+}  // namespace
+
+const char *fdr_prepare(DevicePlan *dp) {
+  if (dp->is_double || fdr_disabled()) return nullptr;
+  // the dropped stop-band images sit at the plan's attenuation: only where that is far below the
+  // float32 noise floor (VHQ-class filters), unless asked for explicitly
+  const char *env = std::getenv("B200SOXR_FDR_ALL");
+  const bool any_precision = env && env[0] == '1';
+  if (!any_precision && !dp->plan.is_double) return nullptr;
+  return prepare_cfg<FdrCfg160_147>(dp, 1);
+}
+
+const char *fdr_run(const DevicePlan &dp, const FdrInfo &fi, const SigDesc &in, const SigDesc &out, long o0, long o1,
+                    unsigned n_sig, unsigned group, cudaStream_t st) {
+  if (o1 <= o0 || !n_sig) return nullptr;
+  if (o0 < fi.n_head) {
+    // the first outputs, where the reference's intermediate signal starts at index 0 (cr.c:487-490)
+    if (dp.plan.stages.size() != 2) return "internal: fdr head needs a two-stage plan";
+    const Stage &sa = dp.plan.stages[0], &sb = dp.plan.stages[1];
+    FdrHeadParams hp;
+    hp.in = in;
+    hp.out = out;
+    hp.n_sig = n_sig;
+    hp.o0 = o0;
+    hp.o1 = std::min<long>(o1, fi.n_head);
+    hp.gA = dp.stages[0].g.as<float>();
+    hp.gB = dp.stages[1].g.as<float>();
+    hp.nA = int(sa.g.size()); hp.nB = int(sb.g.size());
+    hp.LA = sa.L; hp.MA = sa.M; hp.LB = sb.L; hp.MB = sb.M;
+    hp.CA = sa.C; hp.CB = sb.C;
+    hp.n_u = fi.n_u;
+    k_fdr_head<<<(n_sig + 3) / 4, 128, 0, st>>>(hp);
+    B2_COUNT_LAUNCH();
+    B2_CUDA(cudaGetLastError());
+    o0 = fi.n_head;
+    if (o1 <= o0) return nullptr;
+  }
+  FdrKParams P;
+  P.in = in;
+  P.out = out;
+  if (!group || n_sig % group) group = n_sig;
+  P.group = group;
+  P.ppg = (group + 1) / 2;
+  P.n_pairs = (n_sig / group) * P.ppg;
+  P.b_first = o0 / fi.adv_out;
+  P.n_blocks = int((o1 - 1) / fi.adv_out - P.b_first + 1);
+  P.o0 = o0;
+  P.o1 = o1;
+  P.H = fi.H.p;
+  P.ftw2 = fi.ftw.p;
+  P.ftw3 = static_cast<const char *>(fi.ftw.p) + size_t(fi.ftw3_off) * sizeof(float2);
+  P.itw2 = fi.itw.p;
+  P.itw3 = static_cast<const char *>(fi.itw.p) + size_t(fi.itw3_off) * sizeof(float2);
+  const long long n_items = (long long)P.n_pairs * P.n_blocks;
+  switch (fi.variant) {
+    case 1: return launch_cfg<FdrCfg160_147>(fi, P, n_items, st);
+  }
+  return "internal: unknown fdr variant";
+}
+
+}  // namespace b2

@@ -1,0 +1,394 @@
+// fdr_stage.cuh -- single-pass frequency-domain rational resampler ("fdr").
+//
+// For a plan whose stages are all rational (cr.c:264-496: DFT stage L1/M1 followed by the
+// vpoly0 stage L2/M2, poly-fir0.h:24-44) the cascade is ONE zero-phase linear operator
+//
+//     out[n] = sum_k c[Mt n - Lt k] in[k],   c = (g1 upsampled by L2) * g2,  Lt = L1 L2, Mt = M1 M2
+//
+// (SURVEY.md 8a-R0).  With lr/mr = Lt/Mt reduced and block sizes NIN = mr a, NOUT = lr a, a block
+// of the operator is evaluated as  IFFT_NOUT( H .* FFT_NIN(in)[remapped bins] ):  one forward
+// transform, one REAL spectrum product (c is symmetric, the block grid keeps its centre on a
+// sample of both rates) and one inverse transform -- instead of the reference's FFT + spectrum
+// replication + larger inverse FFT (cr.c:87-146) followed by a 20-tap polyphase dot product per
+// output (poly-fir0.h:24-28).  The terms it drops are the images the reference folds back from
+// its own stop band (below -att dB); it is used for batches where att >= 150 dB (VHQ) so the
+// difference to the reference is ~1e-9 RMS, far inside the 1e-6 budget.  Blocks overlap by one
+// grid step (mr input / lr output samples) on each side, enough for the composite filter's
+// half-width; the first few outputs of a stream, where the reference's intermediate signal does
+// not exist before index 0 (cr.c:487-490), are recomputed by the exact direct-form kernels.
+//
+// FFTs: N = RA*RB*RC, three register-radix passes (decimation in time forward, the mirrored
+// decimation in frequency backward) with shared-memory exchanges whose strides are chosen so
+// that every access is bank-conflict free (scratch/fdr_bank_sim.py); radices 12/14/20 are
+// prime-factor compositions of 3/4/5/7 (fft_regs.cuh) -- PFFFT's radix-3/5 passes are compiled
+// out in libsoxr (pffft.c:320,424), its block sizes being powers of two.
+#pragma once
+#include "fft_regs.cuh"
+#include "fft_stage.cuh"
+
+namespace b2 {
+
+enum { kP2JFast = 0, kP2Row16 = 1 };
+
+// Three-pass FFT of N = RA*RB*RC points on a thread group.
+//   E1[S1*j + g]      g = RC*m' + m in [0, RB*RC), j in [0, RA)      between passes 1 and 2
+//   E2[S2*m + t2]     t2 = j + RA*q2 in [0, RA*RB), m in [0, RC)      between passes 2 and 3
+// Pass-2 threads: MODE kP2JFast: tau = j + RA*m;  kP2Row16: j = tau >> 4, m = tau & 15 (RC <= 16).
+template <int RA_, int RB_, int RC_, int S1_, int S2_, int MODE_>
+struct Fft3 {
+  static constexpr int RA = RA_, RB = RB_, RC = RC_, S1 = S1_, S2 = S2_, MODE = MODE_;
+  static constexpr int N = RA * RB * RC, G1 = RB * RC, T3 = RA * RB;
+  static constexpr int T2 = MODE == kP2Row16 ? 16 * RA : RA * RC;
+  static constexpr int E1_ELEMS = S1 * RA, E2_ELEMS = S2 * RC;
+  static constexpr int TW2_ELEMS = RB * RA, TW3_ELEMS = RC * T3;
+
+  static __host__ __device__ __forceinline__ bool p2_map(int tau, int &j, int &m) {
+    if (MODE == kP2Row16) {
+      j = tau >> 4;
+      m = tau & 15;
+      return j < RA && m < RC;
+    }
+    j = tau % RA;
+    m = tau / RA;
+    return m < RC;
+  }
+
+  // ---- forward (DIT): x natural -> X natural ---------------------------------------------
+  // pass 1: Z[j; g] = sum_n w_RA^(n j) x[g + G1 n];  ld(g, n) returns x[g + G1 n] (n is a compile-time
+  // constant after unrolling, so callers can fold G1 * n into an immediate offset)
+  template <int TP, typename C, typename LD>
+  static __host__ __device__ __forceinline__ void fwd_p1(int tau, C *__restrict__ E1, LD ld) {
+    constexpr int NU = (G1 + TP - 1) / TP;
+    if (tau >= TP) return;
+    C a[NU][RA];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const int g = tau + TP * u;
+      if (NU * TP == G1 || g < G1) {
+#pragma unroll
+        for (int n = 0; n < RA; ++n) a[u][n] = ld(g, n);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const int g = tau + TP * u;
+      if (NU * TP == G1 || g < G1) {
+        Dft<RA>::template run<false>(a[u]);
+#pragma unroll
+        for (int j = 0; j < RA; ++j) E1[S1 * j + g] = a[u][j];
+      }
+    }
+  }
+  // pass 2: Y_m[j + RA q2] = sum_m' w_RB^(m' q2) w_(RA RB)^(j m') Z[j; RC m' + m]
+  // Twiddles are fetched into registers BEFORE the barrier that precedes the pass that uses them (the
+  // registers of the pass just finished are free there), so their latency overlaps the barrier wait.
+  template <typename C>
+  static __host__ __device__ __forceinline__ void ld_tw2(int tau, const C *__restrict__ tw2, C (&w)[RB]) {
+    int j, m;
+    if (!p2_map(tau, j, m)) j = 0;   // idle threads load (and ignore) valid entries: no control flow around w
+    const C *__restrict__ tw = tw2 + j;
+#pragma unroll
+    for (int mp = 1; mp < RB; ++mp) w[mp] = tw[mp * RA];
+  }
+  // entries [M0, M1) only: a pass may prefetch some of its twiddles and fetch the rest itself
+  template <int M0, int M1, typename C>
+  static __host__ __device__ __forceinline__ void ld_tw3(int tau, const C *__restrict__ tw3, C (&w)[RC]) {
+    const int t = tau < T3 ? tau : T3 - 1;
+#pragma unroll
+    for (int m = M0; m < M1; ++m) w[m] = tw3[m * T3 + t];
+  }
+  template <typename R>
+  static __host__ __device__ __forceinline__ void ld_h(int tau, const R *__restrict__ H, R (&h)[RC]) {
+    const int t = tau < T3 ? tau : T3 - 1;
+#pragma unroll
+    for (int q = 0; q < RC; ++q) h[q] = H[t + T3 * q];
+  }
+
+  template <typename C>
+  static __host__ __device__ __forceinline__ void fwd_p2(int tau, const C *__restrict__ E1, C *__restrict__ E2,
+                                                         const C (&w)[RB]) {
+    int j, m;
+    if (!p2_map(tau, j, m)) return;
+    C v[RB];
+    const C *__restrict__ src = E1 + S1 * j + m;
+#pragma unroll
+    for (int mp = 0; mp < RB; ++mp) v[mp] = src[RC * mp];
+#pragma unroll
+    for (int mp = 1; mp < RB; ++mp) v[mp] = cmul(v[mp], w[mp]);
+    Dft<RB>::template run<false>(v);
+    C *__restrict__ dst = E2 + S2 * m + j;
+#pragma unroll
+    for (int q2 = 0; q2 < RB; ++q2) dst[RA * q2] = v[q2];
+  }
+  // pass 3: X[t + T3 q] = sum_m w_RC^(m q) w_N^(t m) Y_m[t]
+  template <int NPRE, typename C>
+  static __host__ __device__ __forceinline__ void fwd_p3(int tau, const C *__restrict__ E2, C *__restrict__ SP,
+                                                         C (&w)[RC], const C *__restrict__ tw3) {
+    if (tau >= T3) return;
+    ld_tw3<NPRE, RC>(tau, tw3, w);
+    C v[RC];
+#pragma unroll
+    for (int m = 0; m < RC; ++m) v[m] = E2[S2 * m + tau];
+#pragma unroll
+    for (int m = 1; m < RC; ++m) v[m] = cmul(v[m], w[m]);
+    Dft<RC>::template run<false>(v);
+#pragma unroll
+    for (int q = 0; q < RC; ++q) SP[tau + T3 * q] = v[q];
+  }
+
+  // ---- inverse (mirrored DIF, unnormalised): Y natural -> y natural ----------------------------
+  // pass 1: reads the forward spectrum of an NIN-point block at the signed frequency of bin F,
+  // times the real filter response H[F].
+  template <int NIN, typename C, typename R>
+  static __host__ __device__ __forceinline__ void inv_p1(int tau, const C *__restrict__ SP, const R (&h)[RC],
+                                                         C *__restrict__ E2, const C *__restrict__ tw3) {
+    if (tau >= T3) return;
+    C v[RC];
+#pragma unroll
+    for (int q = 0; q < RC; ++q) {
+      const int F = tau + T3 * q;
+      const bool pos = ((N / 2) % T3 == 0) ? (q < (N / 2) / T3) : (F < (N + 1) / 2);
+      const int k = pos ? F : F + (NIN - N);
+      v[q] = scale(h[q], SP[k]);
+    }
+    Dft<RC>::template run<true>(v);
+#pragma unroll
+    for (int m = 1; m < RC; ++m) v[m] = cmulc(v[m], tw3[m * T3 + tau]);
+#pragma unroll
+    for (int m = 0; m < RC; ++m) E2[S2 * m + tau] = v[m];
+  }
+  template <typename C>
+  static __host__ __device__ __forceinline__ void inv_p2(int tau, const C *__restrict__ E2, C *__restrict__ E1,
+                                                         const C *__restrict__ tw2) {
+    int j, m;
+    if (!p2_map(tau, j, m)) return;
+    C v[RB];
+    const C *__restrict__ src = E2 + S2 * m + j;
+#pragma unroll
+    for (int q2 = 0; q2 < RB; ++q2) v[q2] = src[RA * q2];
+    Dft<RB>::template run<true>(v);
+    const C *__restrict__ tw = tw2 + j;
+#pragma unroll
+    for (int mp = 1; mp < RB; ++mp) v[mp] = cmulc(v[mp], tw[mp * RA]);
+    C *__restrict__ dst = E1 + S1 * j + m;
+#pragma unroll
+    for (int mp = 0; mp < RB; ++mp) dst[RC * mp] = v[mp];
+  }
+  template <int TP, typename C, typename ST>
+  static __host__ __device__ __forceinline__ void inv_p3(int tau, const C *__restrict__ E1, ST st) {
+    constexpr int NU = (G1 + TP - 1) / TP;
+    if (tau >= TP) return;
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const int g = tau + TP * u;
+      if (NU * TP == G1 || g < G1) {
+        C a[RA];
+#pragma unroll
+        for (int j = 0; j < RA; ++j) a[j] = E1[S1 * j + g];
+        Dft<RA>::template run<true>(a);
+#pragma unroll
+        for (int n = 0; n < RA; ++n) st(g, n, a[n]);
+      }
+    }
+  }
+};
+
+constexpr int fdr_cmax(int a, int b) { return a > b ? a : b; }
+// threads (a multiple of 32) taking part in a pass over G items done in ceil(G / threads) rounds
+constexpr int fdr_tp(int G, int threads) {
+  const int rounds = (G + threads - 1) / threads;
+  const int per = (G + rounds - 1) / rounds;
+  return (per + 31) / 32 * 32;
+}
+
+// One block geometry: NIN = RIN*A in, NOUT = ROUT*A out, OVL grid steps of overlap (half on each side).
+template <class FW_, class IV_, int RIN_, int ROUT_, int OVL_, int THREADS_, int MIN_CTAS_>
+struct FdrCfg {
+  typedef FW_ FW;
+  typedef IV_ IV;
+  static constexpr int RIN = RIN_, ROUT = ROUT_, OVL = OVL_, THREADS = THREADS_, MIN_CTAS = MIN_CTAS_;
+  static constexpr int NIN = FW::N, NOUT = IV::N, A = NIN / RIN;
+  static_assert(NIN == RIN * A && NOUT == ROUT * A && OVL % 2 == 0, "block sizes must share the grid step");
+  static_assert(THREADS % 32 == 0 && THREADS >= FW::T2 && THREADS >= FW::T3 && THREADS >= IV::T2 && THREADS >= IV::T3,
+                "every pass must fit the CTA");
+  static constexpr int M_IN = RIN * OVL / 2, M_OUT = ROUT * OVL / 2;
+  static constexpr int ADV_IN = RIN * (A - OVL), ADV_OUT = ROUT * (A - OVL);
+  static constexpr int TP_F1 = fdr_tp(FW::G1, THREADS), TP_I3 = fdr_tp(IV::G1, THREADS);
+  static constexpr int PRE3 = FW::RC < 20 ? FW::RC : 20;   // forward pass-3 twiddles prefetched across the barrier (register budget)
+  static constexpr int BUF_A = fdr_cmax(fdr_cmax(FW::E1_ELEMS, NIN), IV::E1_ELEMS);
+  static constexpr int BUF_B = fdr_cmax(FW::E2_ELEMS, IV::E2_ELEMS);
+};
+
+// 48000 -> 44100 family (io ratio 160/147): 2560 -> 2352 points
+typedef FdrCfg<Fft3<8, 16, 20, 322, 136, kP2JFast>, Fft3<12, 14, 14, 196, 169, kP2Row16>, 160, 147, 2, 224, 4> FdrCfg160_147;
+
+struct FdrInfo {
+  int variant = 0;          // 1: FdrCfg160_147
+  int n_head = 0;           // outputs [0, n_head) are recomputed by the exact path
+  int adv_out = 0, adv_in = 0, m_in = 0, m_out = 0, nin = 0, nout = 0;
+  size_t smem_bytes = 0;
+  int n_u = 0;              // intermediate samples the head kernel needs
+  DevBuf H, ftw, itw;       // response; forward / inverse twiddles (tw2 then tw3)
+  int ftw3_off = 0, itw3_off = 0;
+  ~FdrInfo() { H.release(); ftw.release(); itw.release(); }
+};
+
+struct FdrKParams {
+  SigDesc in, out;
+  unsigned n_pairs, group, ppg;
+  long b_first;
+  int n_blocks;
+  long o0, o1;
+  const void *H, *ftw2, *ftw3, *itw2, *itw3;
+};
+
+// first outputs of a two-stage cascade, direct form (see k_fdr_head)
+struct FdrHeadParams {
+  SigDesc in, out;
+  unsigned n_sig;
+  long o0, o1;                      // outputs [o0, o1), o1 <= n_head
+  const float *gA, *gB;             // stage taps
+  int nA, nB, LA, MA, LB, MB;
+  long CA, CB;
+  int n_u;                          // intermediate samples u[0 .. n_u) needed
+};
+
+#ifdef __CUDACC__
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKParams P) {
+  typedef float R;
+  typedef float2 C;
+  typedef typename Cfg::FW FW;
+  typedef typename Cfg::IV IV;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C *const bufA = reinterpret_cast<C *>(smem_raw);
+  C *const bufB = bufA + Cfg::BUF_A;
+  const int tau = int(threadIdx.x);
+  const R *__restrict__ H = static_cast<const R *>(P.H);
+  const C *__restrict__ ftw2 = static_cast<const C *>(P.ftw2), *__restrict__ ftw3 = static_cast<const C *>(P.ftw3);
+  const C *__restrict__ itw2 = static_cast<const C *>(P.itw2), *__restrict__ itw3 = static_cast<const C *>(P.itw3);
+
+  // a contiguous range of (pair, block) items per CTA, walked incrementally: the per-pair address
+  // set-up (integer divisions) runs only when the pair changes
+  const unsigned long long n_items = (unsigned long long)P.n_pairs * unsigned(P.n_blocks);
+  const unsigned long long it0 = n_items * blockIdx.x / gridDim.x, it1 = n_items * (blockIdx.x + 1ull) / gridDim.x;
+  unsigned pair = unsigned(it0 / unsigned(P.n_blocks));
+  int bi = int(it0 % unsigned(P.n_blocks));
+  bool fresh = true;
+  // per-pair state
+  PairIn<R> pin;
+  long long ooff0 = 0, ooff1 = 0;
+  bool has1 = false, ovec = false, fast = false;
+  const float2 *src_pair = nullptr;
+  float2 *dst_pair = nullptr;
+
+  for (unsigned long long it = it0; it < it1; ++it) {
+    if (fresh) {
+      const unsigned clip = pair / P.ppg, cp = pair % P.ppg;
+      const unsigned s0 = clip * P.group + 2 * cp, s1 = s0 + 1;
+      has1 = 2 * cp + 1 < P.group;
+      pin = make_pair_in<R>(P.in, s0, has1);
+      ooff0 = (long long)(s0 / P.out.channels) * P.out.clip_stride + (long long)(s0 % P.out.channels) * P.out.chan_stride -
+              P.out.base * P.out.frame_stride;
+      ooff1 = has1 ? (long long)(s1 / P.out.channels) * P.out.clip_stride + (long long)(s1 % P.out.channels) * P.out.chan_stride -
+                         P.out.base * P.out.frame_stride
+                   : ooff0;
+      ovec = P.out.dtype == 0 && has1 && ooff1 == ooff0 + 1 && !(ooff0 & 1) && !(P.out.frame_stride & 1) &&
+             !(reinterpret_cast<unsigned long long>(P.out.p) & 7);
+      // interleaved stereo float32 on both sides: float2 per frame, unit stride
+      fast = pin.vec && ovec && pin.fs == 2 && P.out.frame_stride == 2;
+      src_pair = reinterpret_cast<const float2 *>(static_cast<const float *>(pin.p) + pin.off0);
+      dst_pair = reinterpret_cast<float2 *>(static_cast<float *>(P.out.p) + ooff0);
+      fresh = false;
+    }
+    const long b = P.b_first + bi;
+    const long kb = b * long(Cfg::ADV_IN) - Cfg::M_IN;      // input index of block point 0
+    const long nb = b * long(Cfg::ADV_OUT) - Cfg::M_OUT;    // output index of block point 0
+    const bool interior = kb >= pin.vlo && kb + Cfg::NIN <= pin.vhi;
+
+    if (fast && interior) {
+      const float2 *__restrict__ src = src_pair + kb;
+      FW::template fwd_p1<Cfg::TP_F1>(tau, bufA, [&](int g, int n) { return src[g + FW::G1 * n]; });
+    } else if (pin.vec && interior) {
+      const float2 *__restrict__ src = src_pair + kb * (pin.fs >> 1);
+      const long long st2 = pin.fs >> 1;
+      FW::template fwd_p1<Cfg::TP_F1>(tau, bufA, [&](int g, int n) { return src[(g + FW::G1 * n) * st2]; });
+    } else {
+      FW::template fwd_p1<Cfg::TP_F1>(tau, bufA, [&](int g, int n) { return pin.load(kb + g + FW::G1 * n); });
+    }
+    {
+      C w[FW::RB];
+      FW::ld_tw2(tau, ftw2, w);
+      __syncthreads();
+      FW::fwd_p2(tau, bufA, bufB, w);
+    }
+    {
+      C w[FW::RC];
+      FW::template ld_tw3<1, Cfg::PRE3>(tau, ftw3, w);
+      __syncthreads();
+      FW::template fwd_p3<Cfg::PRE3>(tau, bufB, bufA, w, ftw3);
+    }
+    {
+      R h[IV::RC];
+      IV::ld_h(tau, H, h);
+      __syncthreads();
+      IV::template inv_p1<Cfg::NIN>(tau, bufA, h, bufB, itw3);
+    }
+    __syncthreads();
+    IV::inv_p2(tau, bufB, bufA, itw2);
+    __syncthreads();
+    {
+      // owned outputs: block-local o in [M_OUT, M_OUT + ADV_OUT), clipped to the requested range
+      const int lo = int(max(long(Cfg::M_OUT), P.o0 - nb)), hi = int(min(long(Cfg::M_OUT + Cfg::ADV_OUT), P.o1 - nb));
+      if (fast) {
+        float2 *__restrict__ dst = dst_pair + nb;
+        if (lo == Cfg::M_OUT && hi == Cfg::M_OUT + Cfg::ADV_OUT) {
+          // whole block owned: rows fully inside [M_OUT, M_OUT + ADV_OUT) need no predicate
+          IV::template inv_p3<Cfg::TP_I3>(tau, bufA, [&](int g, int n, C v) {
+            const bool row_in = IV::G1 * n >= Cfg::M_OUT && IV::G1 * (n + 1) <= Cfg::M_OUT + Cfg::ADV_OUT;
+            const int o = g + IV::G1 * n;
+            if (row_in || (o >= Cfg::M_OUT && o < Cfg::M_OUT + Cfg::ADV_OUT)) dst[o] = v;
+          });
+        } else {
+          IV::template inv_p3<Cfg::TP_I3>(tau, bufA, [&](int g, int n, C v) {
+            const int o = g + IV::G1 * n;
+            if (o >= lo && o < hi) dst[o] = v;
+          });
+        }
+      } else if (ovec) {
+        float2 *__restrict__ dst = dst_pair + nb * (P.out.frame_stride >> 1);
+        const long long st2 = P.out.frame_stride >> 1;
+        IV::template inv_p3<Cfg::TP_I3>(tau, bufA, [&](int g, int n, C v) {
+          const int o = g + IV::G1 * n;
+          if (o >= lo && o < hi) dst[o * st2] = v;
+        });
+      } else {
+        IV::template inv_p3<Cfg::TP_I3>(tau, bufA, [&](int g, int n, C v) {
+          const int o = g + IV::G1 * n;
+          if (o >= lo && o < hi) store_pair<R>(P.out, ooff0, ooff1, has1, false, nb + o, v);
+        });
+      }
+    }
+    __syncthreads();   // bufA is rewritten by the next item's first pass
+    if (++bi == P.n_blocks) {
+      bi = 0;
+      ++pair;
+      fresh = true;
+    }
+  }
+}
+#endif  // __CUDACC__
+
+// ---- host side ---------------------------------------------------------------
+// Real zero-phase response of the plan's cascade on the NOUT-bin grid, including every
+// normalisation (kernel output = unnormalised inverse transform of H .* X).  Empty if the plan
+// is not a cascade of rational stages reducing to rin:rout or the composite filter does not fit
+// in the block margins.
+std::vector<double> fdr_response(const Plan &plan, int rin, int rout, int nin, int nout, int m_in, int *n_head);
+
+const char *fdr_prepare(DevicePlan *dp);
+// final outputs [o0, o1) of all signals: k_fdr_head for [o0, n_head), k_fdr for the rest
+const char *fdr_run(const DevicePlan &dp, const FdrInfo &fi, const SigDesc &in, const SigDesc &out, long o0, long o1,
+                    unsigned n_sig, unsigned group, cudaStream_t st);
+
+}  // namespace b2

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <map>
 
+#include "fdr_stage.cuh"
 #include "fft_stage.cuh"
 #include "kernels_generic.cuh"
 
@@ -57,6 +58,14 @@ Workspace::~Workspace() {
   if (h2d_stream) cudaStreamDestroy(h2d_stream);
   if (d2h_stream) cudaStreamDestroy(d2h_stream);
   for (cudaEvent_t e : events) cudaEventDestroy(e);
+  if (busy_ev) cudaEventDestroy(busy_ev);
+}
+
+const char *Workspace::mark_busy(cudaStream_t st) {
+  if (!busy_ev) B2_CUDA(cudaEventCreateWithFlags(&busy_ev, cudaEventDisableTiming));
+  B2_CUDA(cudaEventRecord(busy_ev, st));
+  busy = true;
+  return nullptr;
 }
 
 const char *Workspace::need_events(size_t n) {
@@ -96,17 +105,27 @@ std::mutex g_plan_mu;
 std::map<PlanKey, std::shared_ptr<DevicePlan>> g_plans;
 }  // namespace
 
-Workspace *acquire_workspace() {
+Workspace *acquire_workspace(bool host_wait) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
   {
-    std::lock_guard<std::mutex> l(g_ws_mu);
-    for (size_t i = g_ws_free.size(); i-- > 0;)
-      if (g_ws_free[i]->device == dev) {   // streams and buffers belong to one device
-        Workspace *w = g_ws_free[i];
-        g_ws_free.erase(g_ws_free.begin() + long(i));
-        return w;
+    Workspace *w = nullptr;
+    {
+      std::lock_guard<std::mutex> l(g_ws_mu);
+      for (size_t i = g_ws_free.size(); i-- > 0;)
+        if (g_ws_free[i]->device == dev) {   // streams and buffers belong to one device
+          w = g_ws_free[i];
+          g_ws_free.erase(g_ws_free.begin() + long(i));
+          break;
+        }
+    }
+    if (w) {
+      if (w->busy && host_wait) {
+        cudaEventSynchronize(w->busy_ev);
+        w->busy = false;
       }
+      return w;
+    }
   }
   Workspace *w = new Workspace();
   w->device = dev;
@@ -157,6 +176,7 @@ const char *get_device_plan(double io_ratio, const QSpec &q, const RSpec &r, dou
     if (e) return e;
   }
   if (const char *e = fft_stage_prepare(dp.get())) return e;
+  if (const char *e = fdr_prepare(dp.get())) return e;
   g_plans[key] = dp;
   *out = dp;
   return nullptr;
@@ -365,11 +385,17 @@ const char *run_stage_generic(const DevicePlan &dp, size_t si, SigIn<T> in, SigO
 
 template <typename T>
 const char *run_range_t(const DevicePlan &dp, const SigDesc &in0, long n_in_total, unsigned n_sig, unsigned group, long o0, long o1,
-                        const SigDesc &out0, Workspace *ws, cudaStream_t st) {
+                        const SigDesc &out0, Workspace *ws, cudaStream_t st, unsigned flags) {
   const size_t S = dp.plan.stages.size();
   if (o1 <= o0 || !n_sig) return nullptr;
   SigDesc cur = in0;
   if (n_in_total >= 0) cur.vhi = std::min(cur.vhi, n_in_total);
+  if ((flags & kRunAllowFdr) && !(flags & kRunGeneric) && dp.fdr && sizeof(T) == 4 && n_in_total >= 0 &&
+      out0.dtype <= 1 && in0.base == 0) {
+    // whole signals: single-pass frequency-domain kernel (the first few outputs, where the reference's
+    // intermediate signal is cut at index 0, cr.c:487-490, come from its direct-form head kernel)
+    return fdr_run(dp, *dp.fdr, cur, out0, o0, o1, n_sig, group, st);
+  }
   if (S == 0)   // unity ratio: samples pass through (cr.c:347; zero-extended by flush)
     return sig_copy<T>(cur, out0, o0, o1, n_sig, st);
 
@@ -377,7 +403,7 @@ const char *run_range_t(const DevicePlan &dp, const SigDesc &in0, long n_in_tota
   struct Launch { size_t first, last; bool fft; Range r; };
   std::vector<Launch> launches;
   for (size_t s = 0; s < S; ++s) {
-    const bool use_fft = dp.fft && dp.fft->stage_index == int(s);
+    const bool use_fft = !(flags & kRunGeneric) && dp.fft && dp.fft->stage_index == int(s);
     const size_t last = (use_fft && dp.fft->fused_poly) ? s + 1 : s;
     launches.push_back({s, last, use_fft, {0, 0}});
     s = last;
@@ -431,9 +457,9 @@ const char *run_range_t(const DevicePlan &dp, const SigDesc &in0, long n_in_tota
 }  // namespace
 
 const char *run_range(const DevicePlan &dp, const SigDesc &in, long n_in_total, unsigned n_sig, unsigned group,
-                      long o0, long o1, const SigDesc &out, Workspace *ws, cudaStream_t stream) {
-  return dp.is_double ? run_range_t<double>(dp, in, n_in_total, n_sig, group, o0, o1, out, ws, stream)
-                      : run_range_t<float>(dp, in, n_in_total, n_sig, group, o0, o1, out, ws, stream);
+                      long o0, long o1, const SigDesc &out, Workspace *ws, cudaStream_t stream, unsigned flags) {
+  return dp.is_double ? run_range_t<double>(dp, in, n_in_total, n_sig, group, o0, o1, out, ws, stream, flags)
+                      : run_range_t<float>(dp, in, n_in_total, n_sig, group, o0, o1, out, ws, stream, flags);
 }
 
 long history_needed_from(const DevicePlan &dp, long o) {

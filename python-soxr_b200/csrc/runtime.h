@@ -49,12 +49,14 @@ struct DevStage {
 };
 
 struct FftStageInfo;   // fft_stage.cuh
+struct FdrInfo;        // fdr_stage.cuh
 
 struct DevicePlan {
   Plan plan;
   bool is_double = false;   // ARITHMETIC type of the device path (plan.is_double is the reference's engine)
   std::vector<DevStage> stages;
   std::shared_ptr<FftStageInfo> fft;   // non-null if the fused FFT kernel applies
+  std::shared_ptr<FdrInfo> fdr;        // non-null if the single-pass frequency-domain kernel applies (batches)
   ~DevicePlan();
 };
 
@@ -74,11 +76,18 @@ struct Workspace {
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   std::vector<cudaEvent_t> events;
   const char *need_events(size_t n);
+  // set when a call returned with work still queued that uses the scratch buffers below: the next
+  // user orders itself after `busy_ev` (on its stream, or on the host)
+  cudaEvent_t busy_ev = nullptr;
+  bool busy = false;
+  const char *mark_busy(cudaStream_t st);
   DevBuf in_stage, out_stage, x, y, t0, t1, seeds, blocks, misc;
   PinnedBuf pin_in, pin_out, pin_misc;
   ~Workspace();
 };
-Workspace *acquire_workspace();
+// host_wait: block until queued work of the previous user has finished (callers that pass false
+// order their own stream after Workspace::busy_ev instead)
+Workspace *acquire_workspace(bool host_wait = true);
 void release_workspace(Workspace *);
 
 // User-side layout of a batch of clips.
@@ -112,8 +121,12 @@ inline SigDesc planar_desc(void *p, bool is_double, size_t stride, long base, lo
 // may still arrive, so reading beyond in.vhi is an error).  `out` is a float32 /
 // float64 destination in any layout (element 0 of a signal == output out.base).
 // `group` = channels per clip (n_sig is a multiple of it).
+// `flags`: kRunAllowFdr lets whole-signal (batch / one-shot `resample`) calls use the single-pass
+// frequency-domain kernel (fdr_stage.cuh) when the plan has one; streams never set it, so a stream's
+// result does not depend on how it was chunked.  kRunGeneric forces the direct-form kernels.
+enum { kRunAllowFdr = 1, kRunGeneric = 2 };
 const char *run_range(const DevicePlan &dp, const SigDesc &in, long n_in_total, unsigned n_sig, unsigned group,
-                      long o0, long o1, const SigDesc &out, Workspace *ws, cudaStream_t stream);
+                      long o0, long o1, const SigDesc &out, Workspace *ws, cudaStream_t stream, unsigned flags = 0);
 
 // Lowest input index any output >= o can still depend on (for history trimming).
 long history_needed_from(const DevicePlan &dp, long o);

@@ -28,6 +28,7 @@ _SPLIT = 4
 
 BATCH_DEVICE_PTRS, BATCH_NO_DITHER, BATCH_DOUBLE = 1, 2, 4
 BATCH_EMULATE_CALLS, BATCH_ONESHOT_CALLS, BATCH_SPLIT_SEMANTICS = 8, 16, 32
+BATCH_EXACT_GRID = 64   # reference block grid only: bit-identical to a ResampleStream fed the same input
 RT_DEVICE_IO = 0x100
 
 
@@ -334,7 +335,7 @@ def _make_oneshot(code):
         resample_batch_raw(x.ctypes.data, y.ctypes.data, in_rate=in_rate, out_rate=out_rate, quality=int(quality),
                            dtype_code=code, n_clips=1, channels=ch, ilen=ilen,
                            in_strides=(0, ch, 1), out_strides=(0, ch, 1), olen=total,
-                           flags=BATCH_ONESHOT_CALLS)
+                           flags=BATCH_ONESHOT_CALLS | BATCH_EXACT_GRID)
         return y
     csoxr_oneshot.__name__ = "csoxr_oneshot_" + _DT_NAME[code]
     return csoxr_oneshot

@@ -194,7 +194,11 @@ def test_stream_counts_delays_match_reference(name):
         assert np.allclose(y, soxr.resample(x, s['in_rate'], s['out_rate'], s['quality']), atol=2)
     else:
         assert rms(y - orc) <= TOL_F32
-        assert np.all(y == soxr.resample(x, s['in_rate'], s['out_rate'], s['quality']))
+        # bit-identical to the one-shot driver on the reference's block grid (tests/test_resample.py:109-116);
+        # soxr.resample may take the single-pass frequency-domain kernel (VHQ float32 at 160:147): same
+        # operator, float32 rounding apart
+        assert np.all(y == soxr._resample_oneshot(x, s['in_rate'], s['out_rate'], s['quality']))
+        assert rms(y.astype(np.float64) - soxr.resample(x, s['in_rate'], s['out_rate'], s['quality'])) <= 5e-7
 
 
 @pytest.mark.parametrize('in_rate, out_rate', [(48000, 22050), (8000, 48000)])
@@ -300,3 +304,35 @@ def test_linearity_and_shift_properties_full_size():
     a2 = np.concatenate([np.zeros((160, 2), np.float32), a])
     ya2 = soxr.resample(a2, 48000, 44100, 'VHQ')
     assert rms(ya2[147 + 400:44100 - 400].astype(np.float64) - ya[400:44100 - 147 - 400]) <= 1e-6
+
+
+# ---- single-pass frequency-domain kernel (fdr_stage.cuh): whole-clip float32 VHQ at 160:147 --------
+@pytest.mark.parametrize("length", [1, 2, 7, 100, 2239, 2240, 2241, 2400, 4480, 4481, 12345, 48000])
+@pytest.mark.parametrize("channels", [1, 2, 3])
+def test_fdr_matches_exact_grid_and_oracle(length, channels):
+    x = np.random.default_rng(100 + length + channels).standard_normal((3, length, channels)).astype(np.float32)
+    y = soxr.resample_batch(x, 48000, 44100, 'VHQ')
+    ye = soxr.resample_batch(x, 48000, 44100, 'VHQ', exact_grid=True)
+    assert y.shape == ye.shape == (3, soxr_ext.output_frames(48000, 44100, length), channels)
+    for b in range(3):
+        want = O.resample_f64(x[b], 48000, 44100, O.VHQ)
+        assert rms(y[b].astype(np.float64) - want) <= TOL_F32
+        assert rms(ye[b].astype(np.float64) - want) <= TOL_F32
+        assert np.max(np.abs(y[b].astype(np.float64) - want)) <= 4e-6
+        # the exact-grid path is the stream's: bit-identical to a ResampleStream fed the same clip
+        rs = soxr.ResampleStream(48000, 44100, channels, dtype='float32', quality='VHQ')
+        assert np.all(rs.resample_chunk(x[b], last=True) == ye[b])
+
+
+def test_fdr_layouts_and_one_shot_drivers():
+    x = np.random.default_rng(77).standard_normal((30011, 2)).astype(np.float32)
+    want = O.resample_f64(x, 48000, 44100, O.VHQ)
+    y_div = soxr.resample(x, 48000, 44100, 'VHQ')                        # C order: divide_proc driver
+    y_split = soxr.resample(np.asfortranarray(x), 48000, 44100, 'VHQ')   # Fortran order: split_ch driver
+    y_one = soxr._resample_oneshot(x, 48000, 44100, 'VHQ')               # reference block grid
+    assert np.all(y_div == y_split)
+    for y in (y_div, y_one):
+        assert rms(y.astype(np.float64) - want) <= TOL_F32
+    assert rms(y_div.astype(np.float64) - y_one) <= 5e-7
+    y_m = soxr.resample(x[:, 0].copy(), 48000, 44100, 'VHQ')             # mono 1-D
+    assert rms(y_m.astype(np.float64) - want[:, 0]) <= TOL_F32
