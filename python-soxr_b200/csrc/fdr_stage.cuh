@@ -30,6 +30,23 @@ namespace b2 {
 
 enum { kP2JFast = 0, kP2Row16 = 1 };
 
+// Twiddle set w[m] = w^m, m = 1 .. R-1: the powers of two come from the table (row m at tw[m * stride],
+// correctly rounded), every other one is ONE product  w[m] = w[hi] * w[m - hi]  (hi = top bit of m) of
+// earlier entries, so its error is a sum of popcount(m) roundings and not m times that of w^1.
+// ceil(log2 R) loads on the L1 data pipe + the rest on the FMA pipe replace R-1 loads: the L1 pipe is
+// the busier of the two in k_fdr (profiles/r1j: 68 % vs 40 %).
+__host__ __device__ constexpr int fdr_top_bit(int m) { return m >= 16 ? 16 : m >= 8 ? 8 : m >= 4 ? 4 : m >= 2 ? 2 : 1; }   // m < 32
+template <int R, typename C>
+__host__ __device__ __forceinline__ void twiddle_set(const C *__restrict__ tw, int stride, C (&w)[R]) {
+  static_assert(R <= 32, "fdr_top_bit covers m < 32");
+#pragma unroll
+  for (int m = 1; m < R; ++m)
+    if (fdr_top_bit(m) == m) w[m] = tw[m * stride];
+#pragma unroll
+  for (int m = 3; m < R; ++m)
+    if (fdr_top_bit(m) != m) w[m] = cmul(w[fdr_top_bit(m)], w[m - fdr_top_bit(m)]);
+}
+
 // Three-pass FFT of N = RA*RB*RC points on a thread group.
 //   E1[S1*j + g]      g = RC*m' + m in [0, RB*RC), j in [0, RA)      between passes 1 and 2
 //   E2[S2*m + t2]     t2 = j + RA*q2 in [0, RA*RB), m in [0, RC)      between passes 2 and 3
@@ -86,16 +103,12 @@ struct Fft3 {
   static __host__ __device__ __forceinline__ void ld_tw2(int tau, const C *__restrict__ tw2, C (&w)[RB]) {
     int j, m;
     if (!p2_map(tau, j, m)) j = 0;   // idle threads load (and ignore) valid entries: no control flow around w
-    const C *__restrict__ tw = tw2 + j;
-#pragma unroll
-    for (int mp = 1; mp < RB; ++mp) w[mp] = tw[mp * RA];
+    twiddle_set<RB>(tw2 + j, RA, w);
   }
-  // entries [M0, M1) only: a pass may prefetch some of its twiddles and fetch the rest itself
-  template <int M0, int M1, typename C>
+  template <typename C>
   static __host__ __device__ __forceinline__ void ld_tw3(int tau, const C *__restrict__ tw3, C (&w)[RC]) {
     const int t = tau < T3 ? tau : T3 - 1;
-#pragma unroll
-    for (int m = M0; m < M1; ++m) w[m] = tw3[m * T3 + t];
+    twiddle_set<RC>(tw3 + t, T3, w);
   }
   template <typename R>
   static __host__ __device__ __forceinline__ void ld_h(int tau, const R *__restrict__ H, R (&h)[RC]) {
@@ -121,11 +134,10 @@ struct Fft3 {
     for (int q2 = 0; q2 < RB; ++q2) dst[RA * q2] = v[q2];
   }
   // pass 3: X[t + T3 q] = sum_m w_RC^(m q) w_N^(t m) Y_m[t]
-  template <int NPRE, typename C>
+  template <typename C>
   static __host__ __device__ __forceinline__ void fwd_p3(int tau, const C *__restrict__ E2, C *__restrict__ SP,
-                                                         C (&w)[RC], const C *__restrict__ tw3) {
+                                                         const C (&w)[RC]) {
     if (tau >= T3) return;
-    ld_tw3<NPRE, RC>(tau, tw3, w);
     C v[RC];
 #pragma unroll
     for (int m = 0; m < RC; ++m) v[m] = E2[S2 * m + tau];
@@ -141,7 +153,7 @@ struct Fft3 {
   // times the real filter response H[F].
   template <int NIN, typename C, typename R>
   static __host__ __device__ __forceinline__ void inv_p1(int tau, const C *__restrict__ SP, const R (&h)[RC],
-                                                         C *__restrict__ E2, const C *__restrict__ tw3) {
+                                                         C *__restrict__ E2, const C (&w)[RC]) {
     if (tau >= T3) return;
     C v[RC];
 #pragma unroll
@@ -153,13 +165,13 @@ struct Fft3 {
     }
     Dft<RC>::template run<true>(v);
 #pragma unroll
-    for (int m = 1; m < RC; ++m) v[m] = cmulc(v[m], tw3[m * T3 + tau]);
+    for (int m = 1; m < RC; ++m) v[m] = cmulc(v[m], w[m]);
 #pragma unroll
     for (int m = 0; m < RC; ++m) E2[S2 * m + tau] = v[m];
   }
   template <typename C>
   static __host__ __device__ __forceinline__ void inv_p2(int tau, const C *__restrict__ E2, C *__restrict__ E1,
-                                                         const C *__restrict__ tw2) {
+                                                         const C (&w)[RB]) {
     int j, m;
     if (!p2_map(tau, j, m)) return;
     C v[RB];
@@ -167,9 +179,8 @@ struct Fft3 {
 #pragma unroll
     for (int q2 = 0; q2 < RB; ++q2) v[q2] = src[RA * q2];
     Dft<RB>::template run<true>(v);
-    const C *__restrict__ tw = tw2 + j;
 #pragma unroll
-    for (int mp = 1; mp < RB; ++mp) v[mp] = cmulc(v[mp], tw[mp * RA]);
+    for (int mp = 1; mp < RB; ++mp) v[mp] = cmulc(v[mp], w[mp]);
     C *__restrict__ dst = E1 + S1 * j + m;
 #pragma unroll
     for (int mp = 0; mp < RB; ++mp) dst[RC * mp] = v[mp];
@@ -214,7 +225,6 @@ struct FdrCfg {
   static constexpr int M_IN = RIN * OVL / 2, M_OUT = ROUT * OVL / 2;
   static constexpr int ADV_IN = RIN * (A - OVL), ADV_OUT = ROUT * (A - OVL);
   static constexpr int TP_F1 = fdr_tp(FW::G1, THREADS), TP_I3 = fdr_tp(IV::G1, THREADS);
-  static constexpr int PRE3 = FW::RC < 20 ? FW::RC : 20;   // forward pass-3 twiddles prefetched across the barrier (register budget)
   static constexpr int BUF_A = fdr_cmax(fdr_cmax(FW::E1_ELEMS, NIN), IV::E1_ELEMS);
   static constexpr int BUF_B = fdr_cmax(FW::E2_ELEMS, IV::E2_ELEMS);
 };
@@ -324,18 +334,24 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
     }
     {
       C w[FW::RC];
-      FW::template ld_tw3<1, Cfg::PRE3>(tau, ftw3, w);
+      FW::ld_tw3(tau, ftw3, w);
       __syncthreads();
-      FW::template fwd_p3<Cfg::PRE3>(tau, bufB, bufA, w, ftw3);
+      FW::fwd_p3(tau, bufB, bufA, w);
     }
     {
       R h[IV::RC];
+      C w[IV::RC];
       IV::ld_h(tau, H, h);
+      IV::ld_tw3(tau, itw3, w);
       __syncthreads();
-      IV::template inv_p1<Cfg::NIN>(tau, bufA, h, bufB, itw3);
+      IV::template inv_p1<Cfg::NIN>(tau, bufA, h, bufB, w);
     }
-    __syncthreads();
-    IV::inv_p2(tau, bufB, bufA, itw2);
+    {
+      C w[IV::RB];
+      IV::ld_tw2(tau, itw2, w);
+      __syncthreads();
+      IV::inv_p2(tau, bufB, bufA, w);
+    }
     __syncthreads();
     {
       // owned outputs: block-local o in [M_OUT, M_OUT + ADV_OUT), clipped to the requested range

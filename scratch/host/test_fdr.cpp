@@ -58,7 +58,7 @@ int main(int argc, char **argv) {
       FW::fwd_p1<Cfg::TP_F1>(tau, bufA.data(), [&](int g, int n) { long k = kb + g + FW::G1 * n; return (k >= 0 && k < n_in) ? x[k] : make_double2(0, 0); });
     for (int tau = 0; tau < Cfg::THREADS; ++tau) { double2 w[FW::RB]; FW::ld_tw2(tau, ftw2.data(), w); FW::fwd_p2(tau, bufA.data(), bufB.data(), w); }
     std::vector<double2> sp(Cfg::BUF_A);
-    for (int tau = 0; tau < Cfg::THREADS; ++tau) { double2 w[FW::RC]; FW::ld_tw3<1, Cfg::PRE3>(tau, ftw3.data(), w); FW::fwd_p3<Cfg::PRE3>(tau, bufB.data(), sp.data(), w, ftw3.data()); }
+    for (int tau = 0; tau < Cfg::THREADS; ++tau) { double2 w[FW::RC]; FW::ld_tw3(tau, ftw3.data(), w); FW::fwd_p3(tau, bufB.data(), sp.data(), w); }
     bufA = sp;
     if (b == 1) {   // check the forward transform against the definition at a few bins
       double worst = 0;
@@ -69,9 +69,9 @@ int main(int argc, char **argv) {
       }
       printf("forward FFT check: max err %.3e\n", worst);
     }
-    for (int tau = 0; tau < Cfg::THREADS; ++tau) { double h[IV::RC]; IV::ld_h(tau, H.data(), h); IV::inv_p1<Cfg::NIN>(tau, bufA.data(), h, bufB.data(), itw3.data()); }
+    for (int tau = 0; tau < Cfg::THREADS; ++tau) { double h[IV::RC]; IV::ld_h(tau, H.data(), h); double2 w[IV::RC]; IV::ld_tw3(tau, itw3.data(), w); IV::inv_p1<Cfg::NIN>(tau, bufA.data(), h, bufB.data(), w); }
     std::vector<double2> e1(Cfg::BUF_A);
-    for (int tau = 0; tau < Cfg::THREADS; ++tau) IV::inv_p2(tau, bufB.data(), e1.data(), itw2.data());
+    for (int tau = 0; tau < Cfg::THREADS; ++tau) { double2 w[IV::RB]; IV::ld_tw2(tau, itw2.data(), w); IV::inv_p2(tau, bufB.data(), e1.data(), w); }
     for (int tau = 0; tau < Cfg::THREADS; ++tau)
       IV::inv_p3<Cfg::TP_I3>(tau, e1.data(), [&](int g, int n, double2 v) { const int o = g + IV::G1 * n;
         long nn = nb + o;
