@@ -234,6 +234,24 @@ def main():
     ms_per_step = total_ms_max / args.steps
     value = world * in_samples * args.steps / (total_ms_max * 1e-3) / 1e6
 
+    # the optional final gather of the output shards (NCCL all_gather over NVLink), timed on its own:
+    # `value` is the sharded throughput (no data-path collective)
+    gather_ms = None
+    if dist is not None:
+        from soxr import distributed as sdist
+        full = sdist.gather_shards(y, world * N_CLIPS)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for _ in range(3):
+            full = sdist.gather_shards(y, world * N_CLIPS)
+        g1.record(stream)
+        barrier()
+        tg = torch.tensor([g0.elapsed_time(g1) / 3], dtype=torch.float64, device=dev)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        gather_ms = float(tg.item())
+        del full
+
     # sanity: the result is finite and has signal power (white noise through a unity-gain LPF)
     chk = float(y[:4].double().pow(2).mean().item())
     if not (0.5 < chk < 1.5):
@@ -285,7 +303,9 @@ def main():
         "config": {"workload": WORKLOAD, "clips_per_gpu": N_CLIPS, "frames": FRAMES, "channels": CH,
                    "in_rate": IN_RATE, "out_rate": OUT_RATE, "quality": QUALITY,
                    "l2": "inputs (393 MB) + outputs (361 MB) per step exceed the 126 MB L2; no explicit flush",
-                   "output_msamples_per_s": value * out_frames / FRAMES},
+                   "output_msamples_per_s": value * out_frames / FRAMES,
+                   "sharding": "clips split contiguously over ranks, no data-path collective",
+                   "final_all_gather_ms": gather_ms},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": _traffic(), "kernel": KERNEL_DESC,
                      "kernel_ms_avg": k_avg, "kernel_ms_min": k_ms[0], "kernel_ms_median": k_ms[len(k_ms) // 2],

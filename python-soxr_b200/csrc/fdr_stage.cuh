@@ -230,7 +230,19 @@ struct FdrCfg {
 };
 
 // 48000 -> 44100 family (io ratio 160/147): 2560 -> 2352 points
-typedef FdrCfg<Fft3<8, 16, 20, 322, 136, kP2JFast>, Fft3<12, 14, 14, 196, 169, kP2Row16>, 160, 147, 2, 224, 4> FdrCfg160_147;
+// Tunables (scripts/build_variant.sh overrides them for A/B runs; B200 results in profiles/r1m_ab.log):
+// 192 threads x 5 CTAs per SM (64 registers) and an L2 prefetch of the pair's next block measured best.
+#ifndef B2_FDR_PREFETCH
+#define B2_FDR_PREFETCH 1
+#endif
+#ifndef B2_FDR_THREADS
+#define B2_FDR_THREADS 192
+#endif
+#ifndef B2_FDR_MIN_CTAS
+#define B2_FDR_MIN_CTAS 5
+#endif
+typedef FdrCfg<Fft3<8, 16, 20, 322, 136, kP2JFast>, Fft3<12, 14, 14, 196, 169, kP2Row16>, 160, 147, 2, B2_FDR_THREADS,
+               B2_FDR_MIN_CTAS> FdrCfg160_147;
 
 struct FdrInfo {
   int variant = 0;          // 1: FdrCfg160_147
@@ -318,6 +330,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
 
     if (fast && interior) {
       const float2 *__restrict__ src = src_pair + kb;
+#if B2_FDR_PREFETCH
+      // pull the next block of this pair towards L2 while this one is transformed (one 128-byte line per thread)
+      if (bi + 1 < P.n_blocks && tau * 16 < Cfg::ADV_IN && kb + Cfg::NIN + Cfg::ADV_IN <= pin.vhi)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(src + Cfg::NIN + tau * 16));
+#endif
       FW::template fwd_p1<Cfg::TP_F1>(tau, bufA, [&](int g, int n) { return src[g + FW::G1 * n]; });
     } else if (pin.vec && interior) {
       const float2 *__restrict__ src = src_pair + kb * (pin.fs >> 1);

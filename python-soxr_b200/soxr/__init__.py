@@ -13,6 +13,7 @@ in one launch sequence, accepting numpy arrays or torch CUDA tensors.
 import numpy as np
 
 from . import soxr_ext
+from . import distributed  # noqa: F401  (clip batches sharded over GPUs; torch is imported lazily)
 from .soxr_ext import QQ, LQ, MQ, HQ, VHQ
 from ._version import version as __version__
 

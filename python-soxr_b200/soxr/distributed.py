@@ -1,0 +1,133 @@
+"""soxr.distributed -- batches of independent clips sharded over the GPUs of one box.
+
+Clips (and channels) never interact in the resampling path: the reference keeps one
+resampler state per channel (libsoxr/src/soxr.c:547-560) and python-soxr creates a fresh
+handle per call (src/soxr_ext.cpp:230), so a batch shards by clip with NO data-path
+collective.  One process per GPU (torchrun); `torch.distributed` is used only for
+
+  * the optional final gather of the output shards (NCCL all_gather / gather over NVLink,
+    gloo in the CPU tests), and
+  * barriers / max-over-ranks timing in bench.py.
+
+A single stream (ResampleStream) does not shard: replicas only.
+
+    lo, hi = shard_bounds(n_clips, world, rank)          # contiguous, sizes differ by at most 1
+    y_local = resample_shard(x[lo:hi], 48000, 44100, 'VHQ')
+    y = gather_shards(y_local, n_clips, dst=None)        # every rank gets [n_clips, frames, ch]
+
+or in one call `resample_batch_sharded(x_full_or_local, ...)`.
+"""
+import numpy as np
+
+from . import soxr_ext
+
+
+def shard_bounds(n_clips, world, rank):
+    """Contiguous clip range [lo, hi) of `rank`: the first n_clips % world ranks hold one clip more."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError('rank {} outside world of size {}'.format(rank, world))
+    if n_clips < 0:
+        raise ValueError('negative clip count')
+    q, r = divmod(int(n_clips), int(world))
+    lo = rank * q + min(rank, r)
+    return lo, lo + q + (1 if rank < r else 0)
+
+
+def shard_sizes(n_clips, world):
+    return [hi - lo for lo, hi in (shard_bounds(n_clips, world, r) for r in range(world))]
+
+
+def _dist():
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized():
+        raise RuntimeError('torch.distributed is not initialised (launch with torchrun, one process per GPU)')
+    return dist
+
+
+def resample_shard(x_local, in_rate, out_rate, quality='HQ', out=None, stream=None, _compute=None):
+    """Resample this rank's clips ([clip, frame] or [clip, frame, channel]) on its own GPU.
+    `_compute` replaces the GPU call in the CPU (gloo) tests; the product default has no CPU fallback."""
+    if _compute is not None:
+        return _compute(x_local, in_rate, out_rate, quality)
+    from . import resample_batch
+    if int(x_local.shape[0]) == 0:      # an empty shard (more ranks than clips) launches nothing
+        total = soxr_ext.output_frames(in_rate, out_rate, int(x_local.shape[1]))
+        shape = (0, total) + tuple(x_local.shape[2:])
+        if type(x_local).__module__.startswith('torch'):
+            import torch
+            return torch.empty(shape, dtype=x_local.dtype, device=x_local.device)
+        return np.empty(shape, dtype=x_local.dtype)
+    return resample_batch(x_local, in_rate, out_rate, quality, out=out, stream=stream)
+
+
+def gather_shards(y_local, n_clips, dst=None, group=None):
+    """Final gather of the output shards, in clip order.
+
+    dst=None: every rank receives the whole [n_clips, ...] result (all_gather);
+    dst=r:    only rank r does (others get None).
+    torch tensors stay on their device (NCCL for CUDA tensors); numpy shards go through
+    CPU tensors (gloo).  Equal shards use one all_gather_into_tensor; ragged ones (n_clips not a
+    multiple of the world size) are padded to the largest shard and trimmed afterwards.
+    """
+    import torch
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = shard_sizes(n_clips, world)
+    is_np = isinstance(y_local, np.ndarray)
+    t = torch.from_numpy(np.ascontiguousarray(y_local)) if is_np else y_local.contiguous()
+    if int(t.shape[0]) != sizes[rank]:
+        raise ValueError('rank {} holds {} clips, its shard of {} is {}'.format(rank, int(t.shape[0]), n_clips, sizes[rank]))
+    tail = tuple(t.shape[1:])
+    big = max(sizes)
+    if big == 0:
+        full = t.new_empty((0,) + tail)
+        return full.numpy() if is_np else full
+    send = t
+    if sizes[rank] != big:
+        send = t.new_zeros((big,) + tail)
+        send[:sizes[rank]] = t
+    if dst is None:
+        buf = t.new_empty((world * big,) + tail)
+        dist.all_gather_into_tensor(buf, send, group=group)
+    else:
+        parts = [t.new_empty((big,) + tail) for _ in range(world)] if rank == dst else None
+        dist.gather(send, parts, dst=dst, group=group)
+        if rank != dst:
+            return None
+        buf = torch.cat(parts, 0)
+    if all(s == big for s in sizes):
+        full = buf
+    else:
+        full = torch.cat([buf[r * big:r * big + sizes[r]] for r in range(world)], 0)
+    return full.numpy() if is_np else full
+
+
+def resample_batch_sharded(x, in_rate, out_rate, quality='HQ', gather=None, x_is_local=False, group=None,
+                           _compute=None):
+    """Resample a batch of equal-length clips over all ranks of the process group.
+
+    x: the whole batch (every rank passes the same array and works on its own slice) or, with
+       x_is_local=True, this rank's shard only.
+    gather: None  -> return this rank's output shard (no collective at all);
+            'all' -> all_gather, every rank returns the whole result;
+            int r -> gather to rank r (others return None).
+    """
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if x_is_local:
+        x_local = x
+        import torch
+        n = torch.tensor([int(x.shape[0])], dtype=torch.int64,
+                         device=x.device if type(x).__module__.startswith('torch') else 'cpu')
+        dist.all_reduce(n, group=group)
+        n_clips = int(n.item())
+        if shard_sizes(n_clips, world)[rank] != int(x.shape[0]):
+            raise ValueError('local shards must follow shard_bounds(): contiguous, sizes differing by at most one')
+    else:
+        n_clips = int(x.shape[0])
+        lo, hi = shard_bounds(n_clips, world, rank)
+        x_local = x[lo:hi]
+    y_local = resample_shard(x_local, in_rate, out_rate, quality, _compute=_compute)
+    if gather is None:
+        return y_local
+    return gather_shards(y_local, n_clips, dst=None if gather == 'all' else int(gather), group=group)

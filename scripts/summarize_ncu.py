@@ -29,7 +29,8 @@ hdr = rows[0]
 lines = ["ncu --set full --clock-control none summary of %s" % os.path.basename(rep), ""]
 kn = hdr.index('Kernel Name')
 units = rows[1]
-traffic = None
+traffic = None      # dram bytes per launch of the DOMINANT kernel (longest gpu__time_duration)
+best_dur = -1.0
 for r in rows[2:]:
     lines.append("kernel: %s" % r[kn])
     for k in KEYS:
@@ -39,8 +40,10 @@ for r in rows[2:]:
     try:
         rd, wr = float(r[hdr.index('dram__bytes_read.sum')]), float(r[hdr.index('dram__bytes_write.sum')])
         mult = {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1}[units[hdr.index('dram__bytes_read.sum')]]
-        traffic = (rd + wr) * mult
-        lines.append("  dram bytes read+write per launch: %.1f MB" % (traffic / 1e6))
+        lines.append("  dram bytes read+write per launch: %.1f MB" % ((rd + wr) * mult / 1e6))
+        dur = float(r[hdr.index('gpu__time_duration.sum')])
+        if dur > best_dur:
+            best_dur, traffic, traffic_kernel = dur, (rd + wr) * mult, r[kn]
     except Exception:
         pass
     lines.append("")
@@ -81,5 +84,5 @@ if h is not None:
 open(out, 'w').write("\n".join(lines) + "\n")
 if traffic:
     with open(os.path.join(os.path.dirname(out), 'latest_traffic.json'), 'w') as f:
-        json.dump({"dram_bytes_per_launch": traffic, "source": os.path.basename(out)}, f)
+        json.dump({"dram_bytes_per_launch": traffic, "kernel": traffic_kernel[:80], "source": os.path.basename(out)}, f)
 print("\n".join(lines[:40]))
