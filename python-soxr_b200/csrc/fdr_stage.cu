@@ -200,10 +200,13 @@ const char *launch_cfg(const FdrInfo &fi, const FdrKParams &P, long long n_items
   static int per_sm[16] = {};
   static int sm_count[16] = {};
   const int di = dev & 15;
+  // B200SOXR_FDR_PAD_KB: extra dynamic shared memory per CTA, to study throughput against CTAs per SM
+  static const size_t pad = [] { const char *v = std::getenv("B200SOXR_FDR_PAD_KB"); return v ? size_t(std::atol(v)) << 10 : size_t(0); }();
+  const size_t smem_bytes = fi.smem_bytes + pad;
   if (!attr_set[di]) {
-    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fi.smem_bytes)));
+    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[di], kern, Cfg::THREADS, fi.smem_bytes) != cudaSuccess ||
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[di], kern, Cfg::THREADS, smem_bytes) != cudaSuccess ||
         per_sm[di] < 1) {
       cudaGetLastError();
       per_sm[di] = 1;
@@ -213,7 +216,7 @@ const char *launch_cfg(const FdrInfo &fi, const FdrKParams &P, long long n_items
     attr_set[di] = true;
   }
   const long long grid = std::min<long long>(n_items, (long long)sm_count[di] * per_sm[di]);
-  kern<<<unsigned(grid), Cfg::THREADS, fi.smem_bytes, st>>>(P);
+  kern<<<unsigned(grid), Cfg::THREADS, smem_bytes, st>>>(P);
   B2_COUNT_LAUNCH();
   B2_CUDA(cudaGetLastError());
   return nullptr;

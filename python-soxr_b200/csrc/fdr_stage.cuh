@@ -73,11 +73,13 @@ struct Fft3 {
   // ---- forward (DIT): x natural -> X natural ---------------------------------------------
   // pass 1: Z[j; g] = sum_n w_RA^(n j) x[g + G1 n];  ld(g, n) returns x[g + G1 n] (n is a compile-time
   // constant after unrolling, so callers can fold G1 * n into an immediate offset)
+  // The loads and the butterflies are separate steps so that a kernel can issue the loads of its NEXT block
+  // early (software pipelining across blocks) and keep them in registers.
+  template <int TP> struct P1Regs { static constexpr int NU = (G1 + TP - 1) / TP; };
   template <int TP, typename C, typename LD>
-  static __host__ __device__ __forceinline__ void fwd_p1(int tau, C *__restrict__ E1, LD ld) {
+  static __host__ __device__ __forceinline__ void fwd_p1_load(int tau, C (&a)[(G1 + TP - 1) / TP][RA], LD ld) {
     constexpr int NU = (G1 + TP - 1) / TP;
     if (tau >= TP) return;
-    C a[NU][RA];
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
       const int g = tau + TP * u;
@@ -86,6 +88,11 @@ struct Fft3 {
         for (int n = 0; n < RA; ++n) a[u][n] = ld(g, n);
       }
     }
+  }
+  template <int TP, typename C>
+  static __host__ __device__ __forceinline__ void fwd_p1_run(int tau, C *__restrict__ E1, C (&a)[(G1 + TP - 1) / TP][RA]) {
+    constexpr int NU = (G1 + TP - 1) / TP;
+    if (tau >= TP) return;
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
       const int g = tau + TP * u;
@@ -95,6 +102,12 @@ struct Fft3 {
         for (int j = 0; j < RA; ++j) E1[S1 * j + g] = a[u][j];
       }
     }
+  }
+  template <int TP, typename C, typename LD>
+  static __host__ __device__ __forceinline__ void fwd_p1(int tau, C *__restrict__ E1, LD ld) {
+    C a[(G1 + TP - 1) / TP][RA];
+    fwd_p1_load<TP>(tau, a, ld);
+    fwd_p1_run<TP>(tau, E1, a);
   }
   // pass 2: Y_m[j + RA q2] = sum_m' w_RB^(m' q2) w_(RA RB)^(j m') Z[j; RC m' + m]
   // Twiddles are fetched into registers BEFORE the barrier that precedes the pass that uses them (the
@@ -235,6 +248,9 @@ struct FdrCfg {
 #ifndef B2_FDR_PREFETCH
 #define B2_FDR_PREFETCH 1
 #endif
+#ifndef B2_FDR_STAGGER
+#define B2_FDR_STAGGER 0
+#endif
 #ifndef B2_FDR_THREADS
 #define B2_FDR_THREADS 192
 #endif
@@ -304,6 +320,13 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
   const float2 *src_pair = nullptr;
   float2 *dst_pair = nullptr;
 
+#if B2_FDR_STAGGER
+  // co-resident CTAs (blockIdx.x / #SMs apart) start their identical phase sequences shifted in time
+  {
+    const unsigned slot = blockIdx.x / 148u;
+    for (unsigned k = 0; k < slot; ++k) __nanosleep(B2_FDR_STAGGER);
+  }
+#endif
   for (unsigned long long it = it0; it < it1; ++it) {
     if (fresh) {
       const unsigned clip = pair / P.ppg, cp = pair % P.ppg;
