@@ -196,7 +196,7 @@ const char *launch_cfg(const FdrInfo &fi, const FdrKParams &P, long long n_items
   auto kern = k_fdr<Cfg>;
   int dev = 0;
   cudaGetDevice(&dev);
-  static bool attr_set[16] = {};
+  static bool attr_set[16] = {};   // per instantiation (one set of statics per Cfg)
   static int per_sm[16] = {};
   static int sm_count[16] = {};
   const int di = dev & 15;
@@ -225,12 +225,22 @@ const char *launch_cfg(const FdrInfo &fi, const FdrKParams &P, long long n_items
 
 const char *fdr_prepare(DevicePlan *dp) {
   if (dp->is_double || fdr_disabled()) return nullptr;
-  // the dropped stop-band images sit at the plan's attenuation: only where that is far below the
-  // float32 noise floor (VHQ-class filters), unless asked for explicitly
+  const Plan &pl = dp->plan;
+  // What the single-pass form drops are the aliases a decimating cascade folds back from its own stop band
+  // (<= -att dB).  It is used where that is far below the float32 noise floor (VHQ-class filters), and for
+  // plans that are ONE DFT stage with L/M = 1/2 or 2/1: there the reference itself decimates by truncating
+  // the spectrum (cr.c:163-170) or interpolates by replicating it (cr.c:87-124), i.e. computes the same thing.
   const char *env = std::getenv("B200SOXR_FDR_ALL");
   const bool any_precision = env && env[0] == '1';
-  if (!any_precision && !dp->plan.is_double) return nullptr;
-  return prepare_cfg<FdrCfg160_147>(dp, 1);
+  const bool single_dft = pl.stages.size() == 1 && pl.stages[0].kind == kDft &&
+                          ((pl.stages[0].L == 1 && pl.stages[0].M == 2) || (pl.stages[0].L == 2 && pl.stages[0].M == 1));
+  if (!any_precision && !pl.is_double && !single_dft) return nullptr;
+  if (const char *e = prepare_cfg<FdrCfg160_147>(dp, 1)) return e;
+  if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg147_160>(dp, 2)) return e;
+  if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg2_1>(dp, 3)) return e;
+  if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg1_2>(dp, 4)) return e;
+  if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg2_1w>(dp, 5)) return e;
+  return nullptr;
 }
 
 const char *fdr_run(const DevicePlan &dp, const FdrInfo &fi, const SigDesc &in, const SigDesc &out, long o0, long o1,
@@ -263,10 +273,20 @@ const char *fdr_run(const DevicePlan &dp, const FdrInfo &fi, const SigDesc &in, 
   P.out = out;
   if (!group || n_sig % group) group = n_sig;
   P.group = group;
-  P.ppg = (group + 1) / 2;
-  P.n_pairs = (n_sig / group) * P.ppg;
   P.b_first = o0 / fi.adv_out;
-  P.n_blocks = int((o1 - 1) / fi.adv_out - P.b_first + 1);
+  const int n_blk = int((o1 - 1) / fi.adv_out - P.b_first + 1);
+  // mono signals: two consecutive blocks of one signal share a transform (real / imaginary parts), so a
+  // signal's result still depends on nothing but the signal itself
+  P.bpair = group == 1;
+  if (P.bpair) {
+    P.ppg = 1;
+    P.n_pairs = n_sig;
+    P.n_blocks = (n_blk + 1) / 2;
+  } else {
+    P.ppg = (group + 1) / 2;
+    P.n_pairs = (n_sig / group) * P.ppg;
+    P.n_blocks = n_blk;
+  }
   P.o0 = o0;
   P.o1 = o1;
   P.H = fi.H.p;
@@ -277,6 +297,10 @@ const char *fdr_run(const DevicePlan &dp, const FdrInfo &fi, const SigDesc &in, 
   const long long n_items = (long long)P.n_pairs * P.n_blocks;
   switch (fi.variant) {
     case 1: return launch_cfg<FdrCfg160_147>(fi, P, n_items, st);
+    case 2: return launch_cfg<FdrCfg147_160>(fi, P, n_items, st);
+    case 3: return launch_cfg<FdrCfg2_1>(fi, P, n_items, st);
+    case 4: return launch_cfg<FdrCfg1_2>(fi, P, n_items, st);
+    case 5: return launch_cfg<FdrCfg2_1w>(fi, P, n_items, st);
   }
   return "internal: unknown fdr variant";
 }

@@ -173,6 +173,7 @@ struct Fft3 {
     for (int q = 0; q < RC; ++q) {
       const int F = tau + T3 * q;
       const bool pos = ((N / 2) % T3 == 0) ? (q < (N / 2) / T3) : (F < (N + 1) / 2);
+      // NIN < N (upsampling, N <= 2 NIN): the same map reads the periodic images of the input spectrum, exactly
       const int k = pos ? F : F + (NIN - N);
       v[q] = scale(h[q], SP[k]);
     }
@@ -257,11 +258,24 @@ struct FdrCfg {
 #ifndef B2_FDR_MIN_CTAS
 #define B2_FDR_MIN_CTAS 5
 #endif
-typedef FdrCfg<Fft3<8, 16, 20, 322, 136, kP2JFast>, Fft3<12, 14, 14, 196, 169, kP2Row16>, 160, 147, 2, B2_FDR_THREADS,
-               B2_FDR_MIN_CTAS> FdrCfg160_147;
+typedef Fft3<8, 16, 20, 322, 136, kP2JFast> Fft2560;
+typedef Fft3<12, 14, 14, 196, 169, kP2Row16> Fft2352;
+typedef Fft3<8, 16, 10, 162, 136, kP2JFast> Fft1280;
+// 48000 -> 44100 family (io ratio 160/147): 2560 -> 2352 points, one grid step (160 in / 147 out) of margin per side
+typedef FdrCfg<Fft2560, Fft2352, 160, 147, 2, B2_FDR_THREADS, B2_FDR_MIN_CTAS> FdrCfg160_147;
+// 44100 -> 48000 family (147/160): the same two transforms with their roles swapped
+// (224 threads: the 12-point first pass then runs one task per thread, 72 registers without spills)
+typedef FdrCfg<Fft2352, Fft2560, 147, 160, 2, 224, 4> FdrCfg147_160;
+// 2:1 (96000 -> 48000, ...): 2560 -> 1280 points, 208 input samples of margin per side.  The reference's own
+// 1/2 DFT stage decimates in the frequency domain the same way (spectrum truncation, cr.c:163-170).
+// (HQ-class filters, 389 taps); 288 samples for VHQ-class ones (533 taps).
+typedef FdrCfg<Fft2560, Fft1280, 2, 1, 208, B2_FDR_THREADS, B2_FDR_MIN_CTAS> FdrCfg2_1;
+typedef FdrCfg<Fft2560, Fft1280, 2, 1, 288, B2_FDR_THREADS, B2_FDR_MIN_CTAS> FdrCfg2_1w;
+// 1:2 (48000 -> 96000, ...): 1280 -> 2560 points, 144 input samples of margin per side (HQ and VHQ)
+typedef FdrCfg<Fft1280, Fft2560, 1, 2, 288, 192, 4> FdrCfg1_2;
 
 struct FdrInfo {
-  int variant = 0;          // 1: FdrCfg160_147
+  int variant = 0;          // 1: FdrCfg160_147, 2: FdrCfg147_160, 3: FdrCfg2_1, 4: FdrCfg1_2, 5: FdrCfg2_1w
   int n_head = 0;           // outputs [0, n_head) are recomputed by the exact path
   int adv_out = 0, adv_in = 0, m_in = 0, m_out = 0, nin = 0, nout = 0;
   size_t smem_bytes = 0;
@@ -274,8 +288,9 @@ struct FdrInfo {
 struct FdrKParams {
   SigDesc in, out;
   unsigned n_pairs, group, ppg;
+  int bpair;                        // mono signals: blocks 2i and 2i+1 of ONE signal ride in the real / imaginary parts
   long b_first;
-  int n_blocks;
+  int n_blocks;                     // items per pair (block pairs when bpair)
   long o0, o1;
   const void *H, *ftw2, *ftw3, *itw2, *itw3;
 };
@@ -330,8 +345,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
   for (unsigned long long it = it0; it < it1; ++it) {
     if (fresh) {
       const unsigned clip = pair / P.ppg, cp = pair % P.ppg;
-      const unsigned s0 = clip * P.group + 2 * cp, s1 = s0 + 1;
-      has1 = 2 * cp + 1 < P.group;
+      const unsigned s0 = P.bpair ? pair : clip * P.group + 2 * cp, s1 = s0 + 1;
+      has1 = !P.bpair && 2 * cp + 1 < P.group;
       pin = make_pair_in<R>(P.in, s0, has1);
       ooff0 = (long long)(s0 / P.out.channels) * P.out.clip_stride + (long long)(s0 % P.out.channels) * P.out.chan_stride -
               P.out.base * P.out.frame_stride;
@@ -346,12 +361,34 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
       dst_pair = reinterpret_cast<float2 *>(static_cast<float *>(P.out.p) + ooff0);
       fresh = false;
     }
-    const long b = P.b_first + bi;
+    const long b = P.b_first + (P.bpair ? 2 * bi : bi);
     const long kb = b * long(Cfg::ADV_IN) - Cfg::M_IN;      // input index of block point 0
     const long nb = b * long(Cfg::ADV_OUT) - Cfg::M_OUT;    // output index of block point 0
     const bool interior = kb >= pin.vlo && kb + Cfg::NIN <= pin.vhi;
 
-    if (fast && interior) {
+    if (P.bpair) {
+      // one signal, two consecutive blocks: block b in the real part, block b + 1 in the imaginary part
+      const bool both_in = interior && kb + Cfg::ADV_IN + Cfg::NIN <= pin.vhi && pin.fs == 1;
+      if (both_in && pin.dtype == 0) {
+        const float *__restrict__ src = static_cast<const float *>(pin.p) + pin.off0 + kb;
+        FW::template fwd_p1<Cfg::TP_F1>(tau, bufA, [&](int g, int n) {
+          return make_float2(src[g + FW::G1 * n], src[g + FW::G1 * n + Cfg::ADV_IN]);
+        });
+      } else if (both_in && pin.dtype == 3) {
+        const short *__restrict__ src = static_cast<const short *>(pin.p) + pin.off0 + kb;
+        FW::template fwd_p1<Cfg::TP_F1>(tau, bufA, [&](int g, int n) {
+          return make_float2(float(src[g + FW::G1 * n]), float(src[g + FW::G1 * n + Cfg::ADV_IN]));
+        });
+      } else {
+        FW::template fwd_p1<Cfg::TP_F1>(tau, bufA, [&](int g, int n) {
+          const long k0 = kb + g + FW::G1 * n, k1 = k0 + Cfg::ADV_IN;
+          C c;
+          c.x = (k0 >= pin.vlo && k0 < pin.vhi) ? ld_as<R>(pin.p, pin.dtype, pin.off0 + k0 * pin.fs) : R(0);
+          c.y = (k1 >= pin.vlo && k1 < pin.vhi) ? ld_as<R>(pin.p, pin.dtype, pin.off0 + k1 * pin.fs) : R(0);
+          return c;
+        });
+      }
+    } else if (fast && interior) {
       const float2 *__restrict__ src = src_pair + kb;
 #if B2_FDR_PREFETCH
       // pull the next block of this pair towards L2 while this one is transformed (one 128-byte line per thread)
@@ -396,7 +433,24 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
     {
       // owned outputs: block-local o in [M_OUT, M_OUT + ADV_OUT), clipped to the requested range
       const int lo = int(max(long(Cfg::M_OUT), P.o0 - nb)), hi = int(min(long(Cfg::M_OUT + Cfg::ADV_OUT), P.o1 - nb));
-      if (fast) {
+      if (P.bpair) {
+        const long nb1 = nb + Cfg::ADV_OUT;                  // block b + 1 (imaginary part)
+        const int lo1 = int(max(long(Cfg::M_OUT), P.o0 - nb1)), hi1 = int(min(long(Cfg::M_OUT + Cfg::ADV_OUT), P.o1 - nb1));
+        if (P.out.dtype == 0 && P.out.frame_stride == 1) {
+          float *__restrict__ dst = static_cast<float *>(P.out.p) + ooff0 + nb;
+          IV::template inv_p3<Cfg::TP_I3>(tau, bufA, [&](int g, int n, C v) {
+            const int o = g + IV::G1 * n;
+            if (o >= lo && o < hi) dst[o] = v.x;
+            if (o >= lo1 && o < hi1) dst[o + Cfg::ADV_OUT] = v.y;
+          });
+        } else {
+          IV::template inv_p3<Cfg::TP_I3>(tau, bufA, [&](int g, int n, C v) {
+            const int o = g + IV::G1 * n;
+            if (o >= lo && o < hi) st_as<R>(P.out.p, P.out.dtype, ooff0 + (nb + o) * P.out.frame_stride, v.x);
+            if (o >= lo1 && o < hi1) st_as<R>(P.out.p, P.out.dtype, ooff0 + (nb1 + o) * P.out.frame_stride, v.y);
+          });
+        }
+      } else if (fast) {
         float2 *__restrict__ dst = dst_pair + nb;
         if (lo == Cfg::M_OUT && hi == Cfg::M_OUT + Cfg::ADV_OUT) {
           // whole block owned: rows fully inside [M_OUT, M_OUT + ADV_OUT) need no predicate

@@ -336,3 +336,43 @@ def test_fdr_layouts_and_one_shot_drivers():
     assert rms(y_div.astype(np.float64) - y_one) <= 5e-7
     y_m = soxr.resample(x[:, 0].copy(), 48000, 44100, 'VHQ')             # mono 1-D
     assert rms(y_m.astype(np.float64) - want[:, 0]) <= TOL_F32
+
+
+# ---- the other ratio families of the single-pass kernel, and block-paired mono signals ----------------------
+FDR_FAMILIES = [(44100, 48000, 'VHQ'), (96000, 48000, 'HQ'), (96000, 48000, 'VHQ'), (48000, 96000, 'HQ'),
+                (22050, 44100, 'VHQ'), (44100, 22050, 'MQ')]
+
+
+@pytest.mark.parametrize("in_rate,out_rate,quality", FDR_FAMILIES)
+@pytest.mark.parametrize("length", [1, 5, 300, 2143, 2144, 2145, 4289, 9999, 30000])
+@pytest.mark.parametrize("channels", [1, 2, 3])
+def test_fdr_families_match_exact_grid_and_oracle(in_rate, out_rate, quality, length, channels):
+    x = np.random.default_rng(length + 7 * channels + in_rate).standard_normal((2, length, channels)).astype(np.float32)
+    y = soxr.resample_batch(x, in_rate, out_rate, quality)
+    ye = soxr.resample_batch(x, in_rate, out_rate, quality, exact_grid=True)
+    assert y.shape == ye.shape == (2, soxr_ext.output_frames(in_rate, out_rate, length), channels)
+    q = {'HQ': O.HQ, 'VHQ': O.VHQ, 'MQ': O.MQ}[quality]
+    for b in range(2):
+        want = O.resample_f64(x[b], in_rate, out_rate, q)
+        assert rms(y[b].astype(np.float64) - want) <= TOL_F32
+        assert rms(ye[b].astype(np.float64) - want) <= TOL_F32
+        assert rms(y[b].astype(np.float64) - ye[b]) <= TOL_F32
+    # a mono clip's result (two of its own blocks per transform) does not depend on its batch neighbours
+    if channels == 1:
+        y0 = soxr.resample_batch(x[1:2], in_rate, out_rate, quality)
+        assert np.all(y0[0] == y[1])
+
+
+def test_fdr_mono_int16_batch_cfg4_shape():
+    # BASELINE config 4 in small: int16 96k -> 48k HQ mono clips; against the reference golden drivers' tolerance
+    x = np.round(np.random.default_rng(3).standard_normal((6, 20000)) * 5000).astype(np.int16)
+    y = soxr.resample_batch(x, 96000, 48000, 'HQ')
+    ye = soxr.resample_batch(x, 96000, 48000, 'HQ', exact_grid=True)
+    assert y.dtype == np.int16 and y.shape == (6, 10000)
+    for b in range(6):
+        want = O.resample_f64(x[b].astype(np.float64), 96000, 48000, O.HQ)
+        assert np.max(np.abs(y[b] - want)) <= 2.0          # rounding + TPDF dither (<= 1 LSB each side)
+        assert np.max(np.abs(y[b].astype(np.int64) - ye[b])) <= 2
+    import torch
+    yt = soxr.resample_batch(torch.from_numpy(x).cuda(), 96000, 48000, 'HQ')
+    assert np.all(yt.cpu().numpy() == y)
