@@ -232,17 +232,31 @@ __global__ void k_rint_clip(const T *__restrict__ Y, size_t y_stride, unsigned c
         t = lcg_next(t);
         ran2 = t >> 3;
       }
+      // the group's 16 samples: 16-byte vector loads / stores when the layout allows (float scratch rows are
+      // 64-sample aligned, so this is the common case for whole-clip batches)
+      T x[16];
+      const T *sp = src + i0;
+      if (sizeof(T) == 4 && !(reinterpret_cast<unsigned long long>(sp) & 15)) {
+        const float4 *s4 = reinterpret_cast<const float4 *>(sp);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 t = s4[k];
+          x[4 * k] = T(t.x); x[4 * k + 1] = T(t.y); x[4 * k + 2] = T(t.z); x[4 * k + 3] = T(t.w);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = sp[k];
+      }
+      I v[16];
       bool invalid = false;
-#pragma unroll 4
+#pragma unroll
       for (int k = 0; k < 16; ++k) {
-        double d = double(src[i0 + k]);
+        double d = double(x[k]);
         if (dither) {
           ran1 >>= 3; ran2 >>= 3;
           d = d + (1. / 32) * double(int((ran1 & 31) - (ran2 & 31)));
         }
-        I v;
-        invalid |= rint_sat<BITS>(d, &v);
-        dst[(i0 + k) * frame_stride] = v;
+        invalid |= rint_sat<BITS>(d, &v[k]);
       }
       if (invalid) {   // group redone by RINT_CLIP from the pre-group seed, re-salted (rint-clip.h:37-54,70-73)
         const long long ne = i0 + 16;
@@ -251,16 +265,28 @@ __global__ void k_rint_clip(const T *__restrict__ Y, size_t y_stride, unsigned c
           t = lcg_next(t); ran1 = t >> 3;
           t = lcg_next(t); ran2 = t >> 3;
         }
+#pragma unroll
         for (int k = 0; k < 16; ++k) {
-          double d = double(src[i0 + k]);
+          double d = double(x[k]);
           if (dither) {
             ran1 >>= 3; ran2 >>= 3;
             d = d + (1. / 32) * double(int((ran1 & 31) - (ran2 & 31)));
           }
-          I v;
-          if (rint_sat<BITS>(d, &v)) ++my_clips;
-          dst[(i0 + k) * frame_stride] = v;
+          if (rint_sat<BITS>(d, &v[k])) ++my_clips;
         }
+      }
+      I *dp = dst + i0 * frame_stride;
+      if (frame_stride == 1 && !(reinterpret_cast<unsigned long long>(dp) & 15)) {
+        constexpr int NV = int(16 * sizeof(I) / 16);
+        uint4 pk[NV];
+        I *pv = reinterpret_cast<I *>(pk);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) pv[k] = v[k];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) reinterpret_cast<uint4 *>(dp)[k] = pk[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) dp[k * frame_stride] = v[k];
       }
     } else {           // tail: one RINT_CLIP pass with one ran pair (rint-clip.h:75)
       unsigned long long ran1 = 0, ran2 = 0;
