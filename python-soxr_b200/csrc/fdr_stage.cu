@@ -227,14 +227,21 @@ const char *fdr_prepare(DevicePlan *dp) {
   if (dp->is_double || fdr_disabled()) return nullptr;
   const Plan &pl = dp->plan;
   // What the single-pass form drops are the aliases a decimating cascade folds back from its own stop band
-  // (<= -att dB).  It is used where that is far below the float32 noise floor (VHQ-class filters), and for
-  // plans that are ONE DFT stage with L/M = 1/2 or 2/1: there the reference itself decimates by truncating
-  // the spectrum (cr.c:163-170) or interpolates by replicating it (cr.c:87-124), i.e. computes the same thing.
+  // (<= -att dB, att = (bits + 1) * 6.02 + 6 dB, cr.c:288,359-363).  It is used
+  //  * for HQ/VHQ-class filters (>= 20 bits, att >= 132 dB = 2.5e-7): measured on B200 against the reference,
+  //    float32 HQ 48k<->44.1k: 2.8e-7 RMS with it, 2.3e-7 without (float32 rounding dominates both;
+  //    scratch/gpu_hq_fdr.py), VHQ 1.7e-7 either way; north_star's budget is 1e-6;
+  //  * for plans that are ONE DFT stage with L/M = 1/2 or 2/1 at every quality: there the reference itself
+  //    decimates by truncating the spectrum (cr.c:163-170) or interpolates by replicating it (cr.c:87-124).
+  // B200SOXR_FDR_ALL=1 lifts the precision condition, B200SOXR_FDR_VHQ_ONLY=1 restores the round-1i rule.
   const char *env = std::getenv("B200SOXR_FDR_ALL");
   const bool any_precision = env && env[0] == '1';
+  env = std::getenv("B200SOXR_FDR_VHQ_ONLY");
+  const bool vhq_only = env && env[0] == '1';
   const bool single_dft = pl.stages.size() == 1 && pl.stages[0].kind == kDft &&
                           ((pl.stages[0].L == 1 && pl.stages[0].M == 2) || (pl.stages[0].L == 2 && pl.stages[0].M == 1));
-  if (!any_precision && !pl.is_double && !single_dft) return nullptr;
+  const bool fine_enough = vhq_only ? pl.is_double : pl.precision_bits >= 20;
+  if (!any_precision && !fine_enough && !single_dft) return nullptr;
   if (const char *e = prepare_cfg<FdrCfg160_147>(dp, 1)) return e;
   if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg147_160>(dp, 2)) return e;
   if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg2_1>(dp, 3)) return e;

@@ -239,8 +239,10 @@ struct FdrCfg {
   static constexpr int M_IN = RIN * OVL / 2, M_OUT = ROUT * OVL / 2;
   static constexpr int ADV_IN = RIN * (A - OVL), ADV_OUT = ROUT * (A - OVL);
   static constexpr int TP_F1 = fdr_tp(FW::G1, THREADS), TP_I3 = fdr_tp(IV::G1, THREADS);
-  static constexpr int BUF_A = fdr_cmax(fdr_cmax(FW::E1_ELEMS, NIN), IV::E1_ELEMS);
-  static constexpr int BUF_B = fdr_cmax(FW::E2_ELEMS, IV::E2_ELEMS);
+  // the two exchange buffers swap roles from one block to the next (no barrier between a block's output pass
+  // and the next block's first pass), so both hold the larger of the two layouts
+  static constexpr int BUF_A = fdr_cmax(fdr_cmax(fdr_cmax(FW::E1_ELEMS, NIN), IV::E1_ELEMS), fdr_cmax(FW::E2_ELEMS, IV::E2_ELEMS));
+  static constexpr int BUF_B = BUF_A;
 };
 
 // 48000 -> 44100 family (io ratio 160/147): 2560 -> 2352 points
@@ -314,8 +316,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
   typedef typename Cfg::FW FW;
   typedef typename Cfg::IV IV;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  C *const bufA = reinterpret_cast<C *>(smem_raw);
-  C *const bufB = bufA + Cfg::BUF_A;
+  C *bufA = reinterpret_cast<C *>(smem_raw);
+  C *bufB = bufA + Cfg::BUF_A;
   const int tau = int(threadIdx.x);
   const R *__restrict__ H = static_cast<const R *>(P.H);
   const C *__restrict__ ftw2 = static_cast<const C *>(P.ftw2), *__restrict__ ftw3 = static_cast<const C *>(P.ftw3);
@@ -479,7 +481,14 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
         });
       }
     }
-    __syncthreads();   // bufA is rewritten by the next item's first pass
+    // No barrier here: the next block's first pass writes into what is bufB now, whose last readers (the second
+    // inverse pass) all passed the barrier above; bufA, still being read by slower warps, is not written again
+    // before the barrier that follows that first pass.
+    {
+      C *const t = bufA;
+      bufA = bufB;
+      bufB = t;
+    }
     if (++bi == P.n_blocks) {
       bi = 0;
       ++pair;

@@ -193,6 +193,7 @@ const char *make_plan(double io_ratio, const QSpec &q, const RSpec &r, double mu
   if (!(io_ratio > 0)) return "resampling factor not positive";
 
   P.io_ratio = io_ratio;
+  P.precision_bits = bits;
   P.is_double = !(bits <= 20 && !(q.flags & 16));           // soxr.c:447
   P.engine = P.is_double ? "b200-cr64" : "b200-cr32";
   const int sizeof_real = P.is_double ? 8 : 4;

@@ -55,6 +55,7 @@ struct Stage {
 struct Plan {
   double io_ratio = 1;
   bool is_double = false;     // engine precision: soxr.c:447
+  double precision_bits = 0;  // the quality spec's precision (stop-band attenuation = (bits + 1) * 6.02 dB, cr.c:288)
   int mode = 0, shr = 0, preL = 1, preM = 1, arbL = 1, postL = 1, postM = 1;
   double arbM = 1;
   bool rational = false, upsample = false;

@@ -83,6 +83,24 @@ if want("cfg1"):
                     rms_vs_ref=rms(y, R.resample(x, 48000, 44100, 'HQ')))
     emit(**line)
 
+# ---- cfg2 shape at other qualities / ratios (device resident): the k_fdr families --------------------------
+if want("fam"):
+    g = torch.Generator(device=dev)
+    g.manual_seed(1)
+    for (ir, orr, q, ch) in [(48000, 44100, 'VHQ', 2), (48000, 44100, 'HQ', 2), (44100, 48000, 'VHQ', 2), (44100, 48000, 'HQ', 2),
+                             (96000, 48000, 'HQ', 2), (48000, 96000, 'HQ', 2), (48000, 44100, 'VHQ', 1), (48000, 44100, 'MQ', 2)]:
+        n_in = ir
+        shape = (1024, n_in, ch) if ch > 1 else (1024, n_in)
+        xd = torch.randn(shape, device=dev, generator=g)
+        n_out = soxr.soxr_ext.output_frames(ir, orr, n_in)
+        yd = torch.empty((1024, n_out, ch) if ch > 1 else (1024, n_out), device=dev)
+        tb, tm = dev_time(lambda: soxr.resample_batch(xd, ir, orr, q, out=yd))
+        alg = (xd.numel() + yd.numel()) * 4
+        emit(cfg="fam", what="1024 clips x 1 s x %d ch f32 %d->%d %s, device resident" % (ch, ir, orr, q),
+             gpu_ms_best=tb * 1e3, gpu_msamples_s=xd.numel() / tb / 1e6, achieved_gbs=alg / tb / 1e9,
+             roofline_frac=alg / tb / 1e9 / 6550.7)
+        del xd, yd
+
 # ---- cfg3 -----------------------------------------------------------------------------------------
 if want("cfg3"):
     N = 441000
