@@ -247,6 +247,9 @@ const char *fdr_prepare(DevicePlan *dp) {
   if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg2_1>(dp, 3)) return e;
   if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg1_2>(dp, 4)) return e;
   if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg2_1w>(dp, 5)) return e;
+  if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg3_1>(dp, 6)) return e;
+  if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg1_3>(dp, 7)) return e;
+  if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg441_160>(dp, 8)) return e;
   return nullptr;
 }
 
@@ -308,6 +311,9 @@ const char *fdr_run(const DevicePlan &dp, const FdrInfo &fi, const SigDesc &in, 
     case 3: return launch_cfg<FdrCfg2_1>(fi, P, n_items, st);
     case 4: return launch_cfg<FdrCfg1_2>(fi, P, n_items, st);
     case 5: return launch_cfg<FdrCfg2_1w>(fi, P, n_items, st);
+    case 6: return launch_cfg<FdrCfg3_1>(fi, P, n_items, st);
+    case 7: return launch_cfg<FdrCfg1_3>(fi, P, n_items, st);
+    case 8: return launch_cfg<FdrCfg441_160>(fi, P, n_items, st);
   }
   return "internal: unknown fdr variant";
 }

@@ -173,8 +173,10 @@ struct Fft3 {
     for (int q = 0; q < RC; ++q) {
       const int F = tau + T3 * q;
       const bool pos = ((N / 2) % T3 == 0) ? (q < (N / 2) / T3) : (F < (N + 1) / 2);
-      // NIN < N (upsampling, N <= 2 NIN): the same map reads the periodic images of the input spectrum, exactly
-      const int k = pos ? F : F + (NIN - N);
+      // NIN < N (upsampling): the map reads the periodic images of the input spectrum, exactly (N <= 3 NIN)
+      static_assert(N <= 3 * NIN, "one wrap of the image index");
+      int k = pos ? F : F + (NIN - N);
+      if (N > 2 * NIN) k = pos ? (k >= NIN ? k - NIN : k) : (k < 0 ? k + NIN : k);
       v[q] = scale(h[q], SP[k]);
     }
     Dft<RC>::template run<true>(v);
@@ -263,6 +265,8 @@ struct FdrCfg {
 typedef Fft3<8, 16, 20, 322, 136, kP2JFast> Fft2560;
 typedef Fft3<12, 14, 14, 196, 169, kP2Row16> Fft2352;
 typedef Fft3<8, 16, 10, 162, 136, kP2JFast> Fft1280;
+typedef Fft3<16, 15, 16, 240, 241, kP2Row16> Fft3840;   // all three passes have 240 tasks
+typedef Fft3<12, 21, 14, 294, 253, kP2Row16> Fft3528;
 // 48000 -> 44100 family (io ratio 160/147): 2560 -> 2352 points, one grid step (160 in / 147 out) of margin per side
 typedef FdrCfg<Fft2560, Fft2352, 160, 147, 2, B2_FDR_THREADS, B2_FDR_MIN_CTAS> FdrCfg160_147;
 // 44100 -> 48000 family (147/160): the same two transforms with their roles swapped
@@ -275,9 +279,14 @@ typedef FdrCfg<Fft2560, Fft1280, 2, 1, 208, B2_FDR_THREADS, B2_FDR_MIN_CTAS> Fdr
 typedef FdrCfg<Fft2560, Fft1280, 2, 1, 288, B2_FDR_THREADS, B2_FDR_MIN_CTAS> FdrCfg2_1w;
 // 1:2 (48000 -> 96000, ...): 1280 -> 2560 points, 144 input samples of margin per side (HQ and VHQ)
 typedef FdrCfg<Fft1280, Fft2560, 1, 2, 288, 192, 4> FdrCfg1_2;
+// 3:1 (48000 -> 16000) and 1:3: 3840 <-> 1280 points, 432 / 144 input samples of margin per side (HQ and VHQ)
+typedef FdrCfg<Fft3840, Fft1280, 3, 1, 288, 256, 3> FdrCfg3_1;
+typedef FdrCfg<Fft1280, Fft3840, 1, 3, 288, 256, 3> FdrCfg1_3;
+// 44100 -> 16000 (441/160): 3528 -> 1280 points, one grid step (441 in / 160 out) of margin per side
+typedef FdrCfg<Fft3528, Fft1280, 441, 160, 2, 256, 2> FdrCfg441_160;   // 21-point pass: 128 registers
 
 struct FdrInfo {
-  int variant = 0;          // 1: FdrCfg160_147, 2: FdrCfg147_160, 3: FdrCfg2_1, 4: FdrCfg1_2, 5: FdrCfg2_1w
+  int variant = 0;          // 1: FdrCfg160_147, 2: FdrCfg147_160, 3: FdrCfg2_1, 4: FdrCfg1_2, 5: FdrCfg2_1w, 6: FdrCfg3_1, 7: FdrCfg1_3, 8: FdrCfg441_160
   int n_head = 0;           // outputs [0, n_head) are recomputed by the exact path
   int adv_out = 0, adv_in = 0, m_in = 0, m_out = 0, nin = 0, nout = 0;
   size_t smem_bytes = 0;

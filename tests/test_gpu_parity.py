@@ -340,11 +340,13 @@ def test_fdr_layouts_and_one_shot_drivers():
 
 # ---- the other ratio families of the single-pass kernel, and block-paired mono signals ----------------------
 FDR_FAMILIES = [(44100, 48000, 'VHQ'), (96000, 48000, 'HQ'), (96000, 48000, 'VHQ'), (48000, 96000, 'HQ'),
-                (22050, 44100, 'VHQ'), (44100, 22050, 'MQ')]
+                (22050, 44100, 'VHQ'), (44100, 22050, 'MQ'), (48000, 44100, 'HQ'), (48000, 16000, 'HQ'),
+                (48000, 16000, 'VHQ'), (16000, 48000, 'HQ'), (8000, 24000, 'VHQ'), (44100, 16000, 'HQ'),
+                (44100, 16000, 'VHQ')]
 
 
 @pytest.mark.parametrize("in_rate,out_rate,quality", FDR_FAMILIES)
-@pytest.mark.parametrize("length", [1, 5, 300, 2143, 2144, 2145, 4289, 9999, 30000])
+@pytest.mark.parametrize("length", [1, 5, 300, 2143, 2144, 2145, 2646, 3215, 3217, 4289, 9999, 30000])
 @pytest.mark.parametrize("channels", [1, 2, 3])
 def test_fdr_families_match_exact_grid_and_oracle(in_rate, out_rate, quality, length, channels):
     x = np.random.default_rng(length + 7 * channels + in_rate).standard_normal((2, length, channels)).astype(np.float32)
