@@ -297,6 +297,12 @@ const char *fdr_run(const DevicePlan &dp, const FdrInfo &fi, const SigDesc &in, 
     P.n_pairs = (n_sig / group) * P.ppg;
     P.n_blocks = n_blk;
   }
+  // interleaved stereo float32 on both sides, every pair 8-byte aligned: one float2 per frame, unit stride
+  auto stereo_f32 = [&](const SigDesc &d) {
+    return d.dtype == 0 && d.channels == 2 && group == 2 && d.chan_stride == 1 && d.frame_stride == 2 &&
+           !(d.clip_stride & 1) && !((d.base * d.frame_stride) & 1) && !(reinterpret_cast<unsigned long long>(d.p) & 7);
+  };
+  P.fast = !P.bpair && stereo_f32(in) && stereo_f32(out);
   P.o0 = o0;
   P.o1 = o1;
   P.H = fi.H.p;

@@ -253,6 +253,9 @@ struct FdrCfg {
 #ifndef B2_FDR_PREFETCH
 #define B2_FDR_PREFETCH 1
 #endif
+#ifndef B2_FDR_TMA
+#define B2_FDR_TMA 1
+#endif
 #ifndef B2_FDR_STAGGER
 #define B2_FDR_STAGGER 0
 #endif
@@ -300,6 +303,7 @@ struct FdrKParams {
   SigDesc in, out;
   unsigned n_pairs, group, ppg;
   int bpair;                        // mono signals: blocks 2i and 2i+1 of ONE signal ride in the real / imaginary parts
+  int fast;                         // every pair is interleaved stereo float32 on both sides (checked on the host)
   long b_first;
   int n_blocks;                     // items per pair (block pairs when bpair)
   long o0, o1;
@@ -335,17 +339,51 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
   // a contiguous range of (pair, block) items per CTA, walked incrementally: the per-pair address
   // set-up (integer divisions) runs only when the pair changes
   const unsigned long long n_items = (unsigned long long)P.n_pairs * unsigned(P.n_blocks);
-  const unsigned long long it0 = n_items * blockIdx.x / gridDim.x, it1 = n_items * (blockIdx.x + 1ull) / gridDim.x;
+  const unsigned long long it0 = n_items * blockIdx.x / gridDim.x;
+  const int n_mine = int(n_items * (blockIdx.x + 1ull) / gridDim.x - it0);   // 32-bit loop state: registers are scarce
   unsigned pair = unsigned(it0 / unsigned(P.n_blocks));
   int bi = int(it0 % unsigned(P.n_blocks));
   bool fresh = true;
-  // per-pair state
-  PairIn<R> pin;
-  long long ooff0 = 0, ooff1 = 0;
-  bool has1 = false, ovec = false, fast = false;
+  // Per-pair state kept in registers across blocks: only what the interleaved-stereo fast path needs.  The other
+  // layouts recompute their address set-up (pair_state) where they use it: at 64 registers per thread the full
+  // state lived in local memory, and its reloads were 5 % of the warp stall samples (profiles/r1v).
+  struct PairState {
+    PairIn<R> pin;
+    long long ooff0, ooff1;
+    bool has1, ovec;
+  };
+  auto pair_state = [&](unsigned pr) {
+    PairState ps;
+    const unsigned clip = pr / P.ppg, cp = pr % P.ppg;
+    const unsigned s0 = P.bpair ? pr : clip * P.group + 2 * cp, s1 = s0 + 1;
+    ps.has1 = !P.bpair && 2 * cp + 1 < P.group;
+    ps.pin = make_pair_in<R>(P.in, s0, ps.has1);
+    ps.ooff0 = (long long)(s0 / P.out.channels) * P.out.clip_stride + (long long)(s0 % P.out.channels) * P.out.chan_stride -
+               P.out.base * P.out.frame_stride;
+    ps.ooff1 = ps.has1 ? (long long)(s1 / P.out.channels) * P.out.clip_stride +
+                             (long long)(s1 % P.out.channels) * P.out.chan_stride - P.out.base * P.out.frame_stride
+                       : ps.ooff0;
+    ps.ovec = P.out.dtype == 0 && ps.has1 && ps.ooff1 == ps.ooff0 + 1 && !(ps.ooff0 & 1) && !(P.out.frame_stride & 1) &&
+              !(reinterpret_cast<unsigned long long>(P.out.p) & 7);
+    return ps;
+  };
+  const bool fast = P.fast != 0;   // launch-uniform, lives in the constant bank
   const float2 *src_pair = nullptr;
   float2 *dst_pair = nullptr;
 
+#if B2_FDR_TMA
+  // The next block's input is staged into the exchange buffer that is idle during the last inverse pass by
+  // TMA bulk copies (one per row of the first pass's [RA][G1] view, at the E1 row stride), so the first pass
+  // of the next block runs in place out of shared memory instead of waiting for global loads.
+  __shared__ __align__(8) unsigned long long in_bar;
+  unsigned in_phase = 0;
+  bool staged = false;
+  if (tau == 0) {
+    mbar_init(&in_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+#endif
 #if B2_FDR_STAGGER
   // co-resident CTAs (blockIdx.x / #SMs apart) start their identical phase sequences shifted in time
   {
@@ -353,32 +391,29 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
     for (unsigned k = 0; k < slot; ++k) __nanosleep(B2_FDR_STAGGER);
   }
 #endif
-  for (unsigned long long it = it0; it < it1; ++it) {
+  for (int it = 0; it < n_mine; ++it) {
     if (fresh) {
-      const unsigned clip = pair / P.ppg, cp = pair % P.ppg;
-      const unsigned s0 = P.bpair ? pair : clip * P.group + 2 * cp, s1 = s0 + 1;
-      has1 = !P.bpair && 2 * cp + 1 < P.group;
-      pin = make_pair_in<R>(P.in, s0, has1);
-      ooff0 = (long long)(s0 / P.out.channels) * P.out.clip_stride + (long long)(s0 % P.out.channels) * P.out.chan_stride -
-              P.out.base * P.out.frame_stride;
-      ooff1 = has1 ? (long long)(s1 / P.out.channels) * P.out.clip_stride + (long long)(s1 % P.out.channels) * P.out.chan_stride -
-                         P.out.base * P.out.frame_stride
-                   : ooff0;
-      ovec = P.out.dtype == 0 && has1 && ooff1 == ooff0 + 1 && !(ooff0 & 1) && !(P.out.frame_stride & 1) &&
-             !(reinterpret_cast<unsigned long long>(P.out.p) & 7);
-      // interleaved stereo float32 on both sides: float2 per frame, unit stride
-      fast = pin.vec && ovec && pin.fs == 2 && P.out.frame_stride == 2;
-      src_pair = reinterpret_cast<const float2 *>(static_cast<const float *>(pin.p) + pin.off0);
-      dst_pair = reinterpret_cast<float2 *>(static_cast<float *>(P.out.p) + ooff0);
+      const PairState ps = pair_state(pair);
+      src_pair = reinterpret_cast<const float2 *>(static_cast<const float *>(ps.pin.p) + ps.pin.off0);
+      dst_pair = reinterpret_cast<float2 *>(static_cast<float *>(P.out.p) + ps.ooff0);
       fresh = false;
     }
     const long b = P.b_first + (P.bpair ? 2 * bi : bi);
     const long kb = b * long(Cfg::ADV_IN) - Cfg::M_IN;      // input index of block point 0
     const long nb = b * long(Cfg::ADV_OUT) - Cfg::M_OUT;    // output index of block point 0
-    const bool interior = kb >= pin.vlo && kb + Cfg::NIN <= pin.vhi;
+    const bool interior = kb >= P.in.vlo && kb + Cfg::NIN <= P.in.vhi;
 
+#if B2_FDR_TMA
+    if (staged) {
+      mbar_wait(&in_bar, in_phase);
+      in_phase ^= 1u;
+      const C *__restrict__ stg = bufA;
+      FW::template fwd_p1<Cfg::TP_F1>(tau, bufA, [&](int g, int n) { return stg[FW::S1 * n + g]; });
+    } else
+#endif
     if (P.bpair) {
       // one signal, two consecutive blocks: block b in the real part, block b + 1 in the imaginary part
+      const PairIn<R> pin = pair_state(pair).pin;
       const bool both_in = interior && kb + Cfg::ADV_IN + Cfg::NIN <= pin.vhi && pin.fs == 1;
       if (both_in && pin.dtype == 0) {
         const float *__restrict__ src = static_cast<const float *>(pin.p) + pin.off0 + kb;
@@ -403,16 +438,19 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
       const float2 *__restrict__ src = src_pair + kb;
 #if B2_FDR_PREFETCH
       // pull the next block of this pair towards L2 while this one is transformed (one 128-byte line per thread)
-      if (bi + 1 < P.n_blocks && tau * 16 < Cfg::ADV_IN && kb + Cfg::NIN + Cfg::ADV_IN <= pin.vhi)
+      if (bi + 1 < P.n_blocks && tau * 16 < Cfg::ADV_IN && kb + Cfg::NIN + Cfg::ADV_IN <= P.in.vhi)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(src + Cfg::NIN + tau * 16));
 #endif
       FW::template fwd_p1<Cfg::TP_F1>(tau, bufA, [&](int g, int n) { return src[g + FW::G1 * n]; });
-    } else if (pin.vec && interior) {
-      const float2 *__restrict__ src = src_pair + kb * (pin.fs >> 1);
-      const long long st2 = pin.fs >> 1;
-      FW::template fwd_p1<Cfg::TP_F1>(tau, bufA, [&](int g, int n) { return src[(g + FW::G1 * n) * st2]; });
     } else {
-      FW::template fwd_p1<Cfg::TP_F1>(tau, bufA, [&](int g, int n) { return pin.load(kb + g + FW::G1 * n); });
+      const PairIn<R> pin = pair_state(pair).pin;
+      if (pin.vec && interior) {
+        const float2 *__restrict__ src = src_pair + kb * (pin.fs >> 1);
+        const long long st2 = pin.fs >> 1;
+        FW::template fwd_p1<Cfg::TP_F1>(tau, bufA, [&](int g, int n) { return src[(g + FW::G1 * n) * st2]; });
+      } else {
+        FW::template fwd_p1<Cfg::TP_F1>(tau, bufA, [&](int g, int n) { return pin.load(kb + g + FW::G1 * n); });
+      }
     }
     {
       C w[FW::RB];
@@ -441,10 +479,28 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
       IV::inv_p2(tau, bufB, bufA, w);
     }
     __syncthreads();
+#if B2_FDR_TMA
+    {
+      // bufB's last readers (the second inverse pass) are all past the barrier above; it becomes the next
+      // block's bufA.  Same pair, whole block inside the clip, 16-byte aligned rows: else the next block loads itself.
+      const long kn = kb + Cfg::ADV_IN;
+      staged = fast && !P.bpair && it + 1 < n_mine && bi + 1 < P.n_blocks && kn >= P.in.vlo && kn + Cfg::NIN <= P.in.vhi &&
+               !(reinterpret_cast<unsigned long long>(src_pair + kn) & 15);
+      if (staged && tau == 0) {
+        static_assert(FW::S1 % 2 == 0 && FW::G1 % 2 == 0 && Cfg::BUF_A % 2 == 0, "16-byte rows for the bulk copies");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic accesses to bufB before, async writes after
+        mbar_expect_tx(&in_bar, unsigned(Cfg::NIN * sizeof(C)));
+#pragma unroll
+        for (int n = 0; n < FW::RA; ++n)
+          tma_bulk_g2s(bufB + FW::S1 * n, src_pair + kn + FW::G1 * n, unsigned(FW::G1 * sizeof(C)), &in_bar);
+      }
+    }
+#endif
     {
       // owned outputs: block-local o in [M_OUT, M_OUT + ADV_OUT), clipped to the requested range
       const int lo = int(max(long(Cfg::M_OUT), P.o0 - nb)), hi = int(min(long(Cfg::M_OUT + Cfg::ADV_OUT), P.o1 - nb));
       if (P.bpair) {
+        const long long ooff0 = pair_state(pair).ooff0;
         const long nb1 = nb + Cfg::ADV_OUT;                  // block b + 1 (imaginary part)
         const int lo1 = int(max(long(Cfg::M_OUT), P.o0 - nb1)), hi1 = int(min(long(Cfg::M_OUT + Cfg::ADV_OUT), P.o1 - nb1));
         if (P.out.dtype == 0 && P.out.frame_stride == 1) {
@@ -476,18 +532,21 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
             if (o >= lo && o < hi) dst[o] = v;
           });
         }
-      } else if (ovec) {
-        float2 *__restrict__ dst = dst_pair + nb * (P.out.frame_stride >> 1);
-        const long long st2 = P.out.frame_stride >> 1;
-        IV::template inv_p3<Cfg::TP_I3>(tau, bufA, [&](int g, int n, C v) {
-          const int o = g + IV::G1 * n;
-          if (o >= lo && o < hi) dst[o * st2] = v;
-        });
       } else {
-        IV::template inv_p3<Cfg::TP_I3>(tau, bufA, [&](int g, int n, C v) {
-          const int o = g + IV::G1 * n;
-          if (o >= lo && o < hi) store_pair<R>(P.out, ooff0, ooff1, has1, false, nb + o, v);
-        });
+        const PairState ps = pair_state(pair);
+        if (ps.ovec) {
+          float2 *__restrict__ dst = dst_pair + nb * (P.out.frame_stride >> 1);
+          const long long st2 = P.out.frame_stride >> 1;
+          IV::template inv_p3<Cfg::TP_I3>(tau, bufA, [&](int g, int n, C v) {
+            const int o = g + IV::G1 * n;
+            if (o >= lo && o < hi) dst[o * st2] = v;
+          });
+        } else {
+          IV::template inv_p3<Cfg::TP_I3>(tau, bufA, [&](int g, int n, C v) {
+            const int o = g + IV::G1 * n;
+            if (o >= lo && o < hi) store_pair<R>(P.out, ps.ooff0, ps.ooff1, ps.has1, false, nb + o, v);
+          });
+        }
       }
     }
     // No barrier here: the next block's first pass writes into what is bufB now, whose last readers (the second
