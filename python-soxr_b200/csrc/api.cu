@@ -292,6 +292,12 @@ b200soxr_error_t b200soxr_clear(b200soxr_t p) {
 
 void b200soxr_delete(b200soxr_t p) { delete p; }
 
+// host chunks / results up to this size bypass the copy engines (see b200soxr_process)
+static const size_t kZeroCopyBytes = [] {
+  const char *v = std::getenv("B200SOXR_ZERO_COPY_KB");
+  return size_t(v ? std::max(0L, std::atol(v)) : 256) << 10;
+}();
+
 b200soxr_error_t b200soxr_process(b200soxr_t p, void const *in, size_t ilen0, size_t *idone0, void *out,
                                   size_t olen, size_t *odone0) {
   if (!p) return "null pointer";
@@ -326,6 +332,15 @@ b200soxr_error_t b200soxr_process(b200soxr_t p, void const *in, size_t ilen0, si
       if (split) return p->error = "b200soxr: device I/O supports interleaved layouts only";
       lay.frame_stride = ch; lay.chan_stride = 1;
     } else {
+      if (!split && ilen * ch * isz <= kZeroCopyBytes) {
+        // small chunk (streaming): no DMA at all.  The chunk is copied into pinned host memory that the device
+        // maps at the same address (UVA) and K1 reads it over PCIe: one launch instead of a staged pageable
+        // cudaMemcpy plus a launch.
+        if ((e = ws->pin_in.reserve(ilen * ch * isz))) return p->error = e;
+        std::memcpy(ws->pin_in.p, in, ilen * ch * isz);
+        lay.frame_stride = ch; lay.chan_stride = 1;
+        dev_in = ws->pin_in.p;
+      } else {
       if ((e = ws->in_stage.reserve(ilen * ch * isz))) return p->error = e;
       if (split) {
         const void *const *ptrs = static_cast<const void *const *>(in);
@@ -338,6 +353,7 @@ b200soxr_error_t b200soxr_process(b200soxr_t p, void const *in, size_t ilen0, si
         lay.frame_stride = ch; lay.chan_stride = 1;
       }
       dev_in = ws->in_stage.p;
+      }
     }
     if ((e = convert_in(lay, dev_in, ilen, p->dp->is_double, p->xbuf.p, p->x_cap, size_t(p->x_hi - p->x_base), st)))
       return p->error = e;
@@ -348,6 +364,7 @@ b200soxr_error_t b200soxr_process(b200soxr_t p, void const *in, size_t ilen0, si
 
   // ---- output (soxr.c:664-733): how much the reference would return now
   const size_t odone = p->emu->pull(olen, p->flushing);
+  bool out_zero_copy = false;
   const bool int_out = ot >= B200SOXR_INT32;
   if (odone || (ot == B200SOXR_INT16 && !(p->io.flags & B200SOXR_NO_DITHER))) {
     const size_t es = p->esz(), osz = dtype_size(ot);
@@ -357,7 +374,13 @@ b200soxr_error_t b200soxr_process(b200soxr_t p, void const *in, size_t ilen0, si
     lay.channels = ch;
     void *dev_out = out;
     if (p->device_io) { lay.frame_stride = ch; lay.chan_stride = 1; }
-    else {
+    else if (!split && odone * ch * osz <= kZeroCopyBytes) {
+      // small result: the last kernel writes straight into mapped pinned host memory (K7 fused, no D2H copy)
+      if ((e = ws->pin_out.reserve(std::max<size_t>(1, odone * ch) * osz))) return p->error = e;
+      dev_out = ws->pin_out.p;
+      out_zero_copy = true;
+      lay.frame_stride = ch; lay.chan_stride = 1;
+    } else {
       if ((e = ws->out_stage.reserve(std::max<size_t>(1, odone * ch) * osz))) return p->error = e;
       dev_out = ws->out_stage.p;
       if (split) { lay.frame_stride = 1; lay.chan_stride = (long long)odone; }
@@ -391,7 +414,7 @@ b200soxr_error_t b200soxr_process(b200soxr_t p, void const *in, size_t ilen0, si
                            ws, st)))
         return p->error = e;
     }
-    if (!p->device_io && odone) {
+    if (!p->device_io && odone && !out_zero_copy) {
       if (split) {
         void *const *ptrs = static_cast<void *const *>(out);
         for (unsigned c = 0; c < ch; ++c)
@@ -411,6 +434,7 @@ b200soxr_error_t b200soxr_process(b200soxr_t p, void const *in, size_t ilen0, si
     }
   }
   if (!p->device_io) B2_CUDA(cudaStreamSynchronize(st));
+  if (out_zero_copy && odone) std::memcpy(out, ws->pin_out.p, odone * ch * dtype_size(ot));
   p->out_done += long(odone);
   if (idone0) *idone0 = ilen;
   if (odone0) *odone0 = odone;

@@ -256,9 +256,6 @@ struct FdrCfg {
 #ifndef B2_FDR_TMA
 #define B2_FDR_TMA 1
 #endif
-#ifndef B2_FDR_STAGGER
-#define B2_FDR_STAGGER 0
-#endif
 #ifndef B2_FDR_THREADS
 #define B2_FDR_THREADS 192
 #endif
@@ -383,13 +380,6 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-#endif
-#if B2_FDR_STAGGER
-  // co-resident CTAs (blockIdx.x / #SMs apart) start their identical phase sequences shifted in time
-  {
-    const unsigned slot = blockIdx.x / 148u;
-    for (unsigned k = 0; k < slot; ++k) __nanosleep(B2_FDR_STAGGER);
-  }
 #endif
   for (int it = 0; it < n_mine; ++it) {
     if (fresh) {
