@@ -184,6 +184,17 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = None
+    if world > 1:
+        # one process per GPU: run (and allocate the pinned host buffers of the e2e leg) on the CPUs next to this
+        # rank's GPU, as a multi-GPU launcher would; harmless where the topology is flat or the call is refused
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+            numa = "rank bound to its GPU's CPU set (%d cpus)" % len(os.sched_getaffinity(0))
+        except Exception as exc:       # noqa: BLE001
+            numa = "not bound (%s)" % type(exc).__name__
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -305,7 +316,7 @@ def main():
                    "l2": "inputs (393 MB) + outputs (361 MB) per step exceed the 126 MB L2; no explicit flush",
                    "output_msamples_per_s": value * out_frames / FRAMES,
                    "sharding": "clips split contiguously over ranks, no data-path collective",
-                   "final_all_gather_ms": gather_ms},
+                   "final_all_gather_ms": gather_ms, "cpu_affinity": numa},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": _traffic(), "kernel": KERNEL_DESC,
                      "kernel_ms_avg": k_avg, "kernel_ms_min": k_ms[0], "kernel_ms_median": k_ms[len(k_ms) // 2],

@@ -378,3 +378,17 @@ def test_fdr_mono_int16_batch_cfg4_shape():
     import torch
     yt = soxr.resample_batch(torch.from_numpy(x).cuda(), 96000, 48000, 'HQ')
     assert np.all(yt.cpu().numpy() == y)
+
+
+@pytest.mark.parametrize("in_rate,out_rate,quality,channels,n_clips", [(48000, 44100, 'VHQ', 2, 330), (96000, 48000, 'HQ', 1, 700),
+                                                                       (44100, 48000, 'HQ', 2, 300)])
+def test_fdr_many_blocks_per_cta_is_batch_invariant(in_rate, out_rate, quality, channels, n_clips):
+    # more (pair, block) items than resident CTAs: every CTA walks several consecutive blocks (exchange buffers
+    # swap roles, the next block is staged by TMA).  A clip's result must not depend on where in the batch it sits.
+    x = np.random.default_rng(5).standard_normal((n_clips, 20000, channels)).astype(np.float32)
+    y = soxr.resample_batch(x, in_rate, out_rate, quality)
+    for b in (0, n_clips // 2, n_clips - 1):
+        assert np.all(y[b] == soxr.resample_batch(x[b:b + 1], in_rate, out_rate, quality)[0])
+    q = {'HQ': O.HQ, 'VHQ': O.VHQ}[quality]
+    want = O.resample_f64(x[n_clips - 1], in_rate, out_rate, q)
+    assert rms(y[n_clips - 1].astype(np.float64) - want) <= TOL_F32
