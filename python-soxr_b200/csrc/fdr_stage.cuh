@@ -283,7 +283,7 @@ typedef FdrCfg<Fft1280, Fft2560, 1, 2, 288, 192, 4> FdrCfg1_2;
 typedef FdrCfg<Fft3840, Fft1280, 3, 1, 288, 256, 3> FdrCfg3_1;
 typedef FdrCfg<Fft1280, Fft3840, 1, 3, 288, 256, 3> FdrCfg1_3;
 // 44100 -> 16000 (441/160): 3528 -> 1280 points, one grid step (441 in / 160 out) of margin per side
-typedef FdrCfg<Fft3528, Fft1280, 441, 160, 2, 256, 2> FdrCfg441_160;   // 21-point pass: 128 registers
+typedef FdrCfg<Fft3528, Fft1280, 441, 160, 2, 320, 3> FdrCfg441_160;   // 294 first-pass tasks in one round: 63 registers, no spills
 
 struct FdrInfo {
   int variant = 0;          // 1: FdrCfg160_147, 2: FdrCfg147_160, 3: FdrCfg2_1, 4: FdrCfg1_2, 5: FdrCfg2_1w, 6: FdrCfg3_1, 7: FdrCfg1_3, 8: FdrCfg441_160
