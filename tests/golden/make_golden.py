@@ -57,6 +57,15 @@ VECTOR_CASES = {
     'mq_f32_44k1_48k':              (14, (4000,), 'float32', 44100, 48000, 'MQ', 1.0),
     'qq_f32_44k1_22k05':            (15, (4000,), 'float32', 44100, 22050, 'QQ', 1.0),
     'tiny_f32_48k_44k1_HQ':         (16, (7,), 'float32', 48000, 44100, 'HQ', 1.0),
+    # ratio families of the single-pass frequency-domain kernel, long enough for several blocks
+    'fam_f32_44k1_48k_VHQ_stereo':  (40, (9000, 2), 'float32', 44100, 48000, 'VHQ', 1.0),
+    'fam_f32_48k_44k1_HQ_stereo':   (41, (9000, 2), 'float32', 48000, 44100, 'HQ', 1.0),
+    'fam_f32_96k_48k_VHQ_mono':     (42, (12000,), 'float32', 96000, 48000, 'VHQ', 1.0),
+    'fam_f32_48k_96k_HQ_stereo':    (43, (6000, 2), 'float32', 48000, 96000, 'HQ', 1.0),
+    'fam_f32_48k_16k_HQ_stereo':    (44, (12000, 2), 'float32', 48000, 16000, 'HQ', 1.0),
+    'fam_f32_16k_48k_VHQ_mono':     (45, (5000,), 'float32', 16000, 48000, 'VHQ', 1.0),
+    'fam_f32_44k1_16k_VHQ_3ch':     (46, (12000, 3), 'float32', 44100, 16000, 'VHQ', 1.0),
+    'fam_i16_48k_16k_HQ_stereo':    (47, (9000, 2), 'int16', 48000, 16000, 'HQ', 5000.0),
 }
 
 STREAM_CASES = {
