@@ -250,6 +250,8 @@ const char *fdr_prepare(DevicePlan *dp) {
   if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg3_1>(dp, 6)) return e;
   if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg1_3>(dp, 7)) return e;
   if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg441_160>(dp, 8)) return e;
+  if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg3_2>(dp, 9)) return e;
+  if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg2_3>(dp, 10)) return e;
   return nullptr;
 }
 
@@ -320,6 +322,8 @@ const char *fdr_run(const DevicePlan &dp, const FdrInfo &fi, const SigDesc &in, 
     case 6: return launch_cfg<FdrCfg3_1>(fi, P, n_items, st);
     case 7: return launch_cfg<FdrCfg1_3>(fi, P, n_items, st);
     case 8: return launch_cfg<FdrCfg441_160>(fi, P, n_items, st);
+    case 9: return launch_cfg<FdrCfg3_2>(fi, P, n_items, st);
+    case 10: return launch_cfg<FdrCfg2_3>(fi, P, n_items, st);
   }
   return "internal: unknown fdr variant";
 }

@@ -282,11 +282,14 @@ typedef FdrCfg<Fft1280, Fft2560, 1, 2, 288, 192, 4> FdrCfg1_2;
 // 3:1 (48000 -> 16000) and 1:3: 3840 <-> 1280 points, 432 / 144 input samples of margin per side (HQ and VHQ)
 typedef FdrCfg<Fft3840, Fft1280, 3, 1, 288, 256, 3> FdrCfg3_1;
 typedef FdrCfg<Fft1280, Fft3840, 1, 3, 288, 256, 3> FdrCfg1_3;
+// 3:2 (48000 -> 32000) and 2:3: 3840 <-> 2560 points, 216 / 144 input samples of margin per side (HQ and VHQ)
+typedef FdrCfg<Fft3840, Fft2560, 3, 2, 144, 256, 3> FdrCfg3_2;
+typedef FdrCfg<Fft2560, Fft3840, 2, 3, 144, 256, 3> FdrCfg2_3;
 // 44100 -> 16000 (441/160): 3528 -> 1280 points, one grid step (441 in / 160 out) of margin per side
 typedef FdrCfg<Fft3528, Fft1280, 441, 160, 2, 320, 3> FdrCfg441_160;   // 294 first-pass tasks in one round: 63 registers, no spills
 
 struct FdrInfo {
-  int variant = 0;          // 1: FdrCfg160_147, 2: FdrCfg147_160, 3: FdrCfg2_1, 4: FdrCfg1_2, 5: FdrCfg2_1w, 6: FdrCfg3_1, 7: FdrCfg1_3, 8: FdrCfg441_160
+  int variant = 0;          // 1: FdrCfg160_147, 2: FdrCfg147_160, 3: FdrCfg2_1, 4: FdrCfg1_2, 5: FdrCfg2_1w, 6: FdrCfg3_1, 7: FdrCfg1_3, 8: FdrCfg441_160, 9: FdrCfg3_2, 10: FdrCfg2_3
   int n_head = 0;           // outputs [0, n_head) are recomputed by the exact path
   int adv_out = 0, adv_in = 0, m_in = 0, m_out = 0, nin = 0, nout = 0;
   size_t smem_bytes = 0;
