@@ -68,10 +68,17 @@ __global__ void k_rational(SigIn<T> in, const T *__restrict__ g, int n_g, long C
 // ---- interpolated-coefficient polyphase stage (vpoly1..3, poly-fir.h:89-101):
 // 32.32 fixed-point clock; phase = top `phase_bits` of the fraction, x = the rest.
 // table: [phase][tap][order+1], highest order first.
+// All signals share one clock, so the interpolated coefficients of output n (n_taps Horner evaluations fed by
+// n_taps * (order + 1) scattered table reads, up to 164 kB of table) are computed ONCE per thread, parked in the
+// thread's column of shared memory, and applied to `spb` signals (blockIdx.y selects the group).  The per-output
+// arithmetic is unchanged (Horner in engine precision like the reference, double accumulation), so results do
+// not depend on the grouping.
 template <typename T>
 __global__ void k_poly_interp(SigIn<T> in, const T *__restrict__ table, int n_taps, int order,
                               int phase_bits, unsigned long long at0, unsigned long long step,
-                              int preload, SigOut<T> out, long o0, long n_out, unsigned n_sig) {
+                              int preload, SigOut<T> out, long o0, long n_out, unsigned n_sig, unsigned spb) {
+  extern __shared__ __align__(16) unsigned char poly_smem[];
+  T *vs = reinterpret_cast<T *>(poly_smem) + threadIdx.x;   // v_j at vs[j * blockDim.x]
   const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n_out) return;
   const long n = o0 + i;
@@ -81,14 +88,16 @@ __global__ void k_poly_interp(SigIn<T> in, const T *__restrict__ table, int n_ta
   const int phase = int(frac >> (32 - phase_bits));
   const T x = T(double(unsigned(frac << phase_bits)) * (1. / 4294967296.));
   const T *c = table + size_t(phase) * n_taps * (order + 1);
-  for (unsigned s = blockIdx.y; s < n_sig; s += gridDim.y) {
+  for (int j = 0; j < n_taps; ++j) {
+    const T *cj = c + j * (order + 1);
+    T v = cj[0];
+    for (int o = 1; o <= order; ++o) v = v * x + cj[o];   // Horner in engine precision, as the reference
+    vs[j * blockDim.x] = v;
+  }
+  const unsigned s_end = min(n_sig, (blockIdx.y + 1u) * spb);
+  for (unsigned s = blockIdx.y * spb; s < s_end; ++s) {
     double acc = 0;
-    for (int j = 0; j < n_taps; ++j) {
-      const T *cj = c + j * (order + 1);
-      T v = cj[0];
-      for (int o = 1; o <= order; ++o) v = v * x + cj[o];   // Horner in engine precision, as the reference
-      acc = fma(double(v), double(in.at(s, pos + j)), acc);
-    }
+    for (int j = 0; j < n_taps; ++j) acc = fma(double(vs[j * blockDim.x]), double(in.at(s, pos + j)), acc);
     out.at(s, n) = T(acc);
   }
 }

@@ -370,10 +370,19 @@ const char *run_stage_generic(const DevicePlan &dp, size_t si, SigIn<T> in, SigO
     case kHalf: case kDft: case kPoly:
       k_rational<T><<<grid, 128, 0, st>>>(in, d.g.as<T>(), int(s.g.size()), s.C, s.L, s.M, out, r.lo, n_out, n_sig);
       break;
-    case kPolyInterp:
-      k_poly_interp<T><<<grid, 128, 0, st>>>(in, d.table.as<T>(), s.num_coefs, s.order, s.phase_bits, s.at0_fix,
-                                             s.step_fix, s.dev_preload, out, r.lo, n_out, n_sig);
+    case kPolyInterp: {
+      // signals per block: enough blocks to fill the GPU (148 SMs x 16 resident blocks), at most 16 signals each
+      const unsigned bx = grid.x;
+      const unsigned spb = unsigned(std::max<size_t>(1, std::min<size_t>(16, size_t(n_sig) * bx / 2368)));
+      const dim3 g2(bx, (n_sig + spb - 1) / spb, 1);
+      const size_t smem = size_t(s.num_coefs) * 128 * sizeof(T);
+      if (g2.y > 65535u || smem > 200 * 1024) return "polyphase stage too large for the interpolating kernel";
+      if (smem > 48 * 1024)   // rare: more than 96 (f32) / 48 (f64) taps per phase
+        B2_CUDA(cudaFuncSetAttribute(k_poly_interp<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      k_poly_interp<T><<<g2, 128, smem, st>>>(in, d.table.as<T>(), s.num_coefs, s.order, s.phase_bits, s.at0_fix,
+                                               s.step_fix, s.dev_preload, out, r.lo, n_out, n_sig, spb);
       break;
+    }
     case kCubic:
       k_cubic<T><<<grid, 128, 0, st>>>(in, s.step_fix, s.cubic_mult, out, r.lo, n_out, n_sig);
       break;

@@ -103,6 +103,26 @@ if want("fam"):
              roofline_frac=alg / tb / 1e9 / 6550.7)
         del xd, yd
 
+# ---- plans outside the k_fdr families (exact-grid fused kernel / generic direct-form kernels) -------------
+if want("misc"):
+    g = torch.Generator(device=dev)
+    g.manual_seed(2)
+    for (ir, orr, q, ch, n) in [(44100, 32000, 'HQ', 2, 256), (32000, 44100, 'HQ', 2, 256), (44100, 47999.5, 'VHQ', 2, 256),
+                                (47999, 44100, 'HQ', 2, 256), (48000, 8000, 'HQ', 2, 256), (8000, 48000, 'HQ', 2, 256),
+                                (48000, 44100, 'LQ', 2, 256), (48000, 44100, 'QQ', 2, 256), (44100, 48000, 'VHQ', 2, -256)]:
+        f64 = n < 0
+        n = abs(n)
+        n_in = int(ir)
+        xd = torch.randn((n, n_in, ch), device=dev, generator=g, dtype=torch.float64 if f64 else torch.float32)
+        n_out = soxr.soxr_ext.output_frames(ir, orr, n_in)
+        yd = torch.empty((n, n_out, ch), device=dev, dtype=xd.dtype)
+        tb, tm = dev_time(lambda: soxr.resample_batch(xd, ir, orr, q, out=yd), n=5, warm=2)
+        alg = (xd.numel() + yd.numel()) * xd.element_size()
+        emit(cfg="misc", what="%d clips x 1 s x %d ch %s %s->%s %s, device resident" % (n, ch, str(xd.dtype)[6:], ir, orr, q),
+             gpu_ms_best=tb * 1e3, gpu_msamples_s=xd.numel() / tb / 1e6, achieved_gbs=alg / tb / 1e9,
+             roofline_frac=alg / tb / 1e9 / 6550.7)
+        del xd, yd
+
 # ---- cfg3 -----------------------------------------------------------------------------------------
 if want("cfg3"):
     N = 441000
