@@ -46,7 +46,9 @@ __global__ void k_convert_in(const Tin *__restrict__ in, long long clip_stride, 
 
 // ---- rational stage, direct form:  out[n] = sum_k g[C + M n - L k] in[k]
 // (half-band half-fir.h:38-50, DFT stage cr.c:68-174, vpoly0 poly-fir0.h:24-44)
-template <typename T>
+// A thread produces output n of SPB signals: each tap is loaded once and used SPB times (per signal the order of
+// the accumulation is unchanged, so results do not depend on the grouping).
+template <typename T, int SPB>
 __global__ void k_rational(SigIn<T> in, const T *__restrict__ g, int n_g, long C, int L, int M,
                            SigOut<T> out, long o0, long n_out, unsigned n_sig) {
   const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -57,11 +59,29 @@ __global__ void k_rational(SigIn<T> in, const T *__restrict__ g, int n_g, long C
   long k_lo = t <= 0 ? 0 : (t + L - 1) / L;
   if (k_lo < in.vlo) k_lo = in.vlo;
   if (k_hi > in.vhi - 1) k_hi = in.vhi - 1;
-  for (unsigned s = blockIdx.y; s < n_sig; s += gridDim.y) {
-    double acc = 0;
-    const T *src = in.p + size_t(s) * in.stride - in.base;
-    for (long k = k_lo; k <= k_hi; ++k) acc = fma(double(g[top - L * k]), double(src[k]), acc);
-    out.at(s, n) = T(acc);
+  const T *gp = g + top;
+  for (unsigned s0 = blockIdx.y * unsigned(SPB); s0 < n_sig; s0 += gridDim.y * unsigned(SPB)) {
+    const T *src = in.p + size_t(s0) * in.stride - in.base;
+    double acc[SPB];
+#pragma unroll
+    for (int u = 0; u < SPB; ++u) acc[u] = 0;
+    if (s0 + SPB <= n_sig) {
+      for (long k = k_lo; k <= k_hi; ++k) {
+        const double gk = double(gp[-long(L) * k]);
+#pragma unroll
+        for (int u = 0; u < SPB; ++u) acc[u] = fma(gk, double(src[size_t(u) * in.stride + k]), acc[u]);
+      }
+    } else {
+      for (long k = k_lo; k <= k_hi; ++k) {
+        const double gk = double(gp[-long(L) * k]);
+#pragma unroll
+        for (int u = 0; u < SPB; ++u)
+          if (s0 + u < n_sig) acc[u] = fma(gk, double(src[size_t(u) * in.stride + k]), acc[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < SPB; ++u)
+      if (s0 + u < n_sig) out.at(s0 + u, n) = T(acc[u]);
   }
 }
 

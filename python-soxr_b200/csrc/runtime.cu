@@ -367,13 +367,20 @@ const char *run_stage_generic(const DevicePlan &dp, size_t si, SigIn<T> in, SigO
   if (n_out <= 0 || !n_sig) return nullptr;
   const dim3 grid = grid_for(size_t(n_out), n_sig, 128);
   switch (s.kind) {
-    case kHalf: case kDft: case kPoly:
-      k_rational<T><<<grid, 128, 0, st>>>(in, d.g.as<T>(), int(s.g.size()), s.C, s.L, s.M, out, r.lo, n_out, n_sig);
+    case kHalf: case kDft: case kPoly: {
+      // 8 signals per thread when that still leaves enough blocks to fill the GPU, else one
+      if (size_t(n_sig / 8) * grid.x >= 2368) {
+        const dim3 g8(grid.x, std::min((n_sig + 7) / 8, 65535u), 1);
+        k_rational<T, 8><<<g8, 128, 0, st>>>(in, d.g.as<T>(), int(s.g.size()), s.C, s.L, s.M, out, r.lo, n_out, n_sig);
+      } else {
+        k_rational<T, 1><<<grid, 128, 0, st>>>(in, d.g.as<T>(), int(s.g.size()), s.C, s.L, s.M, out, r.lo, n_out, n_sig);
+      }
       break;
+    }
     case kPolyInterp: {
       // signals per block: enough blocks to fill the GPU (148 SMs x 16 resident blocks), at most 16 signals each
       const unsigned bx = grid.x;
-      const unsigned spb = unsigned(std::max<size_t>(1, std::min<size_t>(16, size_t(n_sig) * bx / 2368)));
+      const unsigned spb = unsigned(std::max<size_t>((n_sig + 65534u) / 65535u, std::min<size_t>(16, size_t(n_sig) * bx / 2368)));
       const dim3 g2(bx, (n_sig + spb - 1) / spb, 1);
       const size_t smem = size_t(s.num_coefs) * 128 * sizeof(T);
       if (g2.y > 65535u || smem > 200 * 1024) return "polyphase stage too large for the interpolating kernel";
