@@ -128,8 +128,9 @@ namespace {
 // out[n] = sum_{m >= 0} gB[CB + MB n - LB m] u[m] (lane n - o0) -- the reference's cascade with its
 // intermediate signal starting at index 0 (cr.c:487-490), in double accumulation like k_rational.
 __global__ void __launch_bounds__(128) k_fdr_head(const FdrHeadParams P) {
-  __shared__ float u_s[4][64];
+  extern __shared__ float u_all[];   // [4 warps][n_u]
   const int w = int(threadIdx.x) >> 5, lane = int(threadIdx.x) & 31;
+  float *u_s = u_all + size_t(w) * size_t(P.n_u);
   const unsigned s = blockIdx.x * 4u + unsigned(w);
   if (s < P.n_sig) {
     const long long off = (long long)(s / P.in.channels) * P.in.clip_stride + (long long)(s % P.in.channels) * P.in.chan_stride -
@@ -144,20 +145,19 @@ __global__ void __launch_bounds__(128) k_fdr_head(const FdrHeadParams P) {
       double acc = 0;
       for (long k = k_lo; k <= k_hi; ++k)
         acc = fma(double(P.gA[top - P.LA * k]), ld_as<double>(P.in.p, P.in.dtype, off + k * P.in.frame_stride), acc);
-      u_s[w][m] = float(acc);
+      u_s[m] = float(acc);
     }
   }
   __syncwarp();
   if (s < P.n_sig) {
-    const long n = P.o0 + lane;
-    if (n < P.o1) {
+    for (long n = P.o0 + lane; n < P.o1; n += 32) {
       const long top = P.CB + long(P.MB) * n;
       long m_hi = top / P.LB;
       const long t = top - (P.nB - 1);
       const long m_lo = t <= 0 ? 0 : (t + P.LB - 1) / P.LB;
       if (m_hi > P.n_u - 1) m_hi = P.n_u - 1;
       double acc = 0;
-      for (long m = m_lo; m <= m_hi; ++m) acc = fma(double(P.gB[top - P.LB * m]), double(u_s[w][m]), acc);
+      for (long m = m_lo; m <= m_hi; ++m) acc = fma(double(P.gB[top - P.LB * m]), double(u_s[m]), acc);
       const long long oo = (long long)(s / P.out.channels) * P.out.clip_stride + (long long)(s % P.out.channels) * P.out.chan_stride +
                            (n - P.out.base) * P.out.frame_stride;
       st_as<double>(P.out.p, P.out.dtype, oo, acc);
@@ -173,11 +173,11 @@ const char *prepare_cfg(DevicePlan *dp, int variant) {
   auto fi = std::make_shared<FdrInfo>();
   fi->variant = variant;
   fi->n_head = n_head;
-  if (n_head > 32) return nullptr;   // one lane per head output
+  if (n_head > 4096) return nullptr;
   if (dp->plan.stages.size() == 2) {
     const Stage &sb = dp->plan.stages[1];
     fi->n_u = int((sb.C + long(sb.M) * std::max(0, n_head - 1)) / sb.L) + 1;
-    if (fi->n_u > 64) return nullptr;
+    if (fi->n_u > 3072) return nullptr;   // k_fdr_head keeps u[0 .. n_u) of 4 signals in 48 kB of shared memory
   }
   fi->adv_in = Cfg::ADV_IN; fi->adv_out = Cfg::ADV_OUT; fi->m_in = Cfg::M_IN; fi->m_out = Cfg::M_OUT;
   fi->nin = Cfg::NIN; fi->nout = Cfg::NOUT;
@@ -252,6 +252,10 @@ const char *fdr_prepare(DevicePlan *dp) {
   if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg441_160>(dp, 8)) return e;
   if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg3_2>(dp, 9)) return e;
   if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg2_3>(dp, 10)) return e;
+  if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg6_1>(dp, 11)) return e;
+  if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg1_6>(dp, 12)) return e;
+  if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg4_1>(dp, 13)) return e;
+  if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg1_4>(dp, 14)) return e;
   return nullptr;
 }
 
@@ -274,7 +278,7 @@ const char *fdr_run(const DevicePlan &dp, const FdrInfo &fi, const SigDesc &in, 
     hp.LA = sa.L; hp.MA = sa.M; hp.LB = sb.L; hp.MB = sb.M;
     hp.CA = sa.C; hp.CB = sb.C;
     hp.n_u = fi.n_u;
-    k_fdr_head<<<(n_sig + 3) / 4, 128, 0, st>>>(hp);
+    k_fdr_head<<<(n_sig + 3) / 4, 128, size_t(4) * size_t(std::max(1, fi.n_u)) * sizeof(float), st>>>(hp);
     B2_COUNT_LAUNCH();
     B2_CUDA(cudaGetLastError());
     o0 = fi.n_head;
@@ -324,6 +328,10 @@ const char *fdr_run(const DevicePlan &dp, const FdrInfo &fi, const SigDesc &in, 
     case 8: return launch_cfg<FdrCfg441_160>(fi, P, n_items, st);
     case 9: return launch_cfg<FdrCfg3_2>(fi, P, n_items, st);
     case 10: return launch_cfg<FdrCfg2_3>(fi, P, n_items, st);
+    case 11: return launch_cfg<FdrCfg6_1>(fi, P, n_items, st);
+    case 12: return launch_cfg<FdrCfg1_6>(fi, P, n_items, st);
+    case 13: return launch_cfg<FdrCfg4_1>(fi, P, n_items, st);
+    case 14: return launch_cfg<FdrCfg1_4>(fi, P, n_items, st);
   }
   return "internal: unknown fdr variant";
 }

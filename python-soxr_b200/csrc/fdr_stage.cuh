@@ -173,10 +173,9 @@ struct Fft3 {
     for (int q = 0; q < RC; ++q) {
       const int F = tau + T3 * q;
       const bool pos = ((N / 2) % T3 == 0) ? (q < (N / 2) / T3) : (F < (N + 1) / 2);
-      // NIN < N (upsampling): the map reads the periodic images of the input spectrum, exactly (N <= 3 NIN)
-      static_assert(N <= 3 * NIN, "one wrap of the image index");
+      // NIN < N (upsampling): the map reads the periodic images of the input spectrum, exactly
       int k = pos ? F : F + (NIN - N);
-      if (N > 2 * NIN) k = pos ? (k >= NIN ? k - NIN : k) : (k < 0 ? k + NIN : k);
+      if (N > 2 * NIN) k = pos ? F % NIN : NIN - 1 - (N - 1 - F) % NIN;
       v[q] = scale(h[q], SP[k]);
     }
     Dft<RC>::template run<true>(v);
@@ -265,6 +264,7 @@ struct FdrCfg {
 typedef Fft3<8, 16, 20, 322, 136, kP2JFast> Fft2560;
 typedef Fft3<12, 14, 14, 196, 169, kP2Row16> Fft2352;
 typedef Fft3<8, 16, 10, 162, 136, kP2JFast> Fft1280;
+typedef Fft3<8, 10, 8, 82, 88, kP2JFast> Fft640;
 typedef Fft3<16, 15, 16, 240, 241, kP2Row16> Fft3840;   // all three passes have 240 tasks
 typedef Fft3<12, 21, 14, 294, 253, kP2Row16> Fft3528;
 // 48000 -> 44100 family (io ratio 160/147): 2560 -> 2352 points, one grid step (160 in / 147 out) of margin per side
@@ -285,11 +285,16 @@ typedef FdrCfg<Fft1280, Fft3840, 1, 3, 288, 256, 3> FdrCfg1_3;
 // 3:2 (48000 -> 32000) and 2:3: 3840 <-> 2560 points, 216 / 144 input samples of margin per side (HQ and VHQ)
 typedef FdrCfg<Fft3840, Fft2560, 3, 2, 144, 256, 3> FdrCfg3_2;
 typedef FdrCfg<Fft2560, Fft3840, 2, 3, 144, 256, 3> FdrCfg2_3;
+// 6:1 (48000 -> 8000: half-band + 1/3 DFT stage), 1:6, 4:1 (48000 -> 12000) and 1:4: 640 points on the low-rate side
+typedef FdrCfg<Fft3840, Fft640, 6, 1, 288, 256, 3> FdrCfg6_1;
+typedef FdrCfg<Fft640, Fft3840, 1, 6, 224, 256, 3> FdrCfg1_6;
+typedef FdrCfg<Fft2560, Fft640, 4, 1, 224, 192, 4> FdrCfg4_1;
+typedef FdrCfg<Fft640, Fft2560, 1, 4, 208, 192, 4> FdrCfg1_4;
 // 44100 -> 16000 (441/160): 3528 -> 1280 points, one grid step (441 in / 160 out) of margin per side
 typedef FdrCfg<Fft3528, Fft1280, 441, 160, 2, 320, 3> FdrCfg441_160;   // 294 first-pass tasks in one round: 63 registers, no spills
 
 struct FdrInfo {
-  int variant = 0;          // 1: FdrCfg160_147, 2: FdrCfg147_160, 3: FdrCfg2_1, 4: FdrCfg1_2, 5: FdrCfg2_1w, 6: FdrCfg3_1, 7: FdrCfg1_3, 8: FdrCfg441_160, 9: FdrCfg3_2, 10: FdrCfg2_3
+  int variant = 0;          // 1: FdrCfg160_147, 2: FdrCfg147_160, 3: FdrCfg2_1, 4: FdrCfg1_2, 5: FdrCfg2_1w, 6: FdrCfg3_1, 7: FdrCfg1_3, 8: FdrCfg441_160, 9: FdrCfg3_2, 10: FdrCfg2_3, 11: FdrCfg6_1, 12: FdrCfg1_6, 13: FdrCfg4_1, 14: FdrCfg1_4
   int n_head = 0;           // outputs [0, n_head) are recomputed by the exact path
   int adv_out = 0, adv_in = 0, m_in = 0, m_out = 0, nin = 0, nout = 0;
   size_t smem_bytes = 0;

@@ -90,7 +90,8 @@ if want("fam"):
     for (ir, orr, q, ch) in [(48000, 44100, 'VHQ', 2), (48000, 44100, 'HQ', 2), (44100, 48000, 'VHQ', 2), (44100, 48000, 'HQ', 2),
                              (96000, 48000, 'HQ', 2), (48000, 96000, 'HQ', 2), (48000, 44100, 'VHQ', 1), (48000, 44100, 'MQ', 2),
                              (48000, 16000, 'HQ', 2), (16000, 48000, 'HQ', 2), (44100, 16000, 'HQ', 2), (44100, 16000, 'VHQ', 1),
-                             (48000, 32000, 'HQ', 2), (32000, 48000, 'HQ', 2)]:
+                             (48000, 32000, 'HQ', 2), (32000, 48000, 'HQ', 2),
+                             (48000, 8000, 'HQ', 2), (8000, 48000, 'HQ', 2), (48000, 12000, 'HQ', 2), (12000, 48000, 'HQ', 2)]:
         n_in = ir
         shape = (1024, n_in, ch) if ch > 1 else (1024, n_in)
         xd = torch.randn(shape, device=dev, generator=g)

@@ -342,7 +342,8 @@ def test_fdr_layouts_and_one_shot_drivers():
 FDR_FAMILIES = [(44100, 48000, 'VHQ'), (96000, 48000, 'HQ'), (96000, 48000, 'VHQ'), (48000, 96000, 'HQ'),
                 (22050, 44100, 'VHQ'), (44100, 22050, 'MQ'), (48000, 44100, 'HQ'), (48000, 16000, 'HQ'),
                 (48000, 16000, 'VHQ'), (16000, 48000, 'HQ'), (8000, 24000, 'VHQ'), (44100, 16000, 'HQ'),
-                (44100, 16000, 'VHQ'), (48000, 32000, 'HQ'), (32000, 48000, 'VHQ')]
+                (44100, 16000, 'VHQ'), (48000, 32000, 'HQ'), (32000, 48000, 'VHQ'),
+                (48000, 8000, 'HQ'), (48000, 8000, 'VHQ'), (8000, 48000, 'HQ'), (48000, 12000, 'HQ'), (12000, 48000, 'HQ')]
 
 
 @pytest.mark.parametrize("in_rate,out_rate,quality", FDR_FAMILIES)
