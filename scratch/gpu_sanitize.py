@@ -6,7 +6,9 @@ sys.path.insert(0, os.path.join(ROOT, "python-soxr_b200"))
 import soxr
 rng = np.random.default_rng(3)
 for (ir, orr, q, ch) in [(48000, 44100, 'VHQ', 2), (48000, 44100, 'VHQ', 1), (44100, 48000, 'VHQ', 2), (96000, 48000, 'HQ', 1),
-                         (48000, 16000, 'HQ', 2), (16000, 48000, 'HQ', 3), (44100, 16000, 'HQ', 2)]:
+                         (48000, 16000, 'HQ', 2), (16000, 48000, 'HQ', 3), (44100, 16000, 'HQ', 2),
+                         (48000, 32000, 'HQ', 2), (32000, 48000, 'VHQ', 1), (48000, 8000, 'HQ', 2), (48000, 8000, 'VHQ', 1),
+                         (8000, 48000, 'HQ', 2), (48000, 12000, 'HQ', 3), (12000, 48000, 'HQ', 1)]:
     x = rng.standard_normal((2, 9000, ch)).astype(np.float32)
     y = soxr.resample_batch(x, ir, orr, q)
     print(ir, orr, q, ch, y.shape, float(np.abs(y).max()))
