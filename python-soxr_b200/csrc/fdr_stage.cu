@@ -224,6 +224,53 @@ __global__ void __launch_bounds__(128) k_fdr_head_split(const FdrHeadParams P) {
   }
 }
 
+// Long heads (e.g. 102 outputs at 48k -> 8k, each a 609-tap dot product): cheaper the other way round.  k_fdr
+// computes the head outputs like any other (the ideal operator, whose intermediate signal u has a run-in
+// u[m], m_min <= m < 0, from the first stage's filter reaching back before the stream), and this kernel
+// subtracts what the reference does not have (its u starts at index 0, cr.c:487-490):
+//     out[n] -= sum_{m_min <= m < 0} gB[CB + MB n - LB m] u[m],   u[m] = sum_{k >= 0} gA[CA + MA m - LA k] x[k].
+// One warp per signal; u[m_min .. 0) in shared memory.
+__global__ void __launch_bounds__(128) k_fdr_head_fix(const FdrHeadParams P) {
+  extern __shared__ float u_neg[];   // [4 warps][-m_min]
+  const int w = int(threadIdx.x) >> 5, lane = int(threadIdx.x) & 31;
+  const int n_neg = -P.m_min;
+  float *u_s = u_neg + size_t(w) * size_t(n_neg);
+  const unsigned s = blockIdx.x * 4u + unsigned(w);
+  if (s < P.n_sig) {
+    const long long off = (long long)(s / P.in.channels) * P.in.clip_stride + (long long)(s % P.in.channels) * P.in.chan_stride -
+                          P.in.base * P.in.frame_stride;
+    for (int i = lane; i < n_neg; i += 32) {
+      const long top = P.CA + long(P.MA) * (P.m_min + i);   // >= 0 by the choice of m_min
+      long k_hi = top / P.LA;
+      const long t = top - (P.nA - 1);
+      long k_lo = t <= 0 ? 0 : (t + P.LA - 1) / P.LA;
+      if (k_lo < P.in.vlo) k_lo = P.in.vlo;
+      if (k_hi > P.in.vhi - 1) k_hi = P.in.vhi - 1;
+      double acc = 0;
+      for (long k = k_lo; k <= k_hi; ++k)
+        acc = fma(double(P.gA[top - P.LA * k]), ld_as<double>(P.in.p, P.in.dtype, off + k * P.in.frame_stride), acc);
+      u_s[i] = float(acc);
+    }
+  }
+  __syncwarp();
+  if (s < P.n_sig) {
+    for (long n = P.o0 + lane; n < P.o1; n += 32) {
+      const long top = P.CB + long(P.MB) * n;
+      long m_hi = top / P.LB;
+      if (m_hi > -1) m_hi = -1;
+      long m_lo = long(ceil_div_ll(top - (P.nB - 1), P.LB));
+      if (m_lo < P.m_min) m_lo = P.m_min;
+      double acc = 0;
+      for (long m = m_lo; m <= m_hi; ++m) acc = fma(double(P.gB[top - P.LB * m]), double(u_s[m - P.m_min]), acc);
+      if (m_lo <= m_hi) {
+        const long long oo = (long long)(s / P.out.channels) * P.out.clip_stride + (long long)(s % P.out.channels) * P.out.chan_stride +
+                             (n - P.out.base) * P.out.frame_stride;
+        st_as<double>(P.out.p, P.out.dtype, oo, ld_as<double>(P.out.p, P.out.dtype, oo) - acc);
+      }
+    }
+  }
+}
+
 template <class Cfg>
 const char *prepare_cfg(DevicePlan *dp, int variant) {
   int n_head = 0;
@@ -236,7 +283,14 @@ const char *prepare_cfg(DevicePlan *dp, int variant) {
   if (dp->plan.stages.size() == 2) {
     const Stage &sb = dp->plan.stages[1];
     fi->n_u = int((sb.C + long(sb.M) * std::max(0, n_head - 1)) / sb.L) + 1;
-    if (fi->n_u > 3072) return nullptr;   // k_fdr_head keeps u[0 .. n_u) of 4 signals in 48 kB of shared memory
+    // long heads: is it cheaper to let k_fdr compute them and subtract the first stage's run-in (k_fdr_head_fix)?
+    const Stage &sa = dp->plan.stages[0];
+    fi->m_min = -int(sa.C / sa.M);
+    const double tapsA = double(sa.g.size()) / sa.L, tapsB = double(sb.g.size()) / sb.L, n_neg = double(-fi->m_min);
+    const double cost_direct = fi->n_u * tapsA + n_head * tapsB;
+    const double cost_fix = n_neg * tapsA * .5 + n_head * std::min(tapsB, n_neg);
+    fi->head_by_fix = n_head > 32 && fi->m_min < 0 && 2 * cost_fix < cost_direct && -fi->m_min <= 3072 && n_head < Cfg::ADV_OUT;
+    if (!fi->head_by_fix && fi->n_u > 3072) return nullptr;   // k_fdr_head keeps u[0 .. n_u) of 4 signals in 48 kB of shared memory
   }
   fi->adv_in = Cfg::ADV_IN; fi->adv_out = Cfg::ADV_OUT; fi->m_in = Cfg::M_IN; fi->m_out = Cfg::M_OUT;
   fi->nin = Cfg::NIN; fi->nout = Cfg::NOUT;
@@ -318,10 +372,24 @@ const char *fdr_prepare(DevicePlan *dp) {
   return nullptr;
 }
 
+static const char *launch_variant(const FdrInfo &fi, const FdrKParams &P, long long n_items, cudaStream_t st);
+
 const char *fdr_run(const DevicePlan &dp, const FdrInfo &fi, const SigDesc &in, const SigDesc &out, long o0, long o1,
                     unsigned n_sig, unsigned group, cudaStream_t st) {
   if (o1 <= o0 || !n_sig) return nullptr;
-  if (o0 < fi.n_head) {
+  FdrHeadParams fix;
+  bool fix_after = false;
+  if (o0 < fi.n_head && fi.head_by_fix && dp.plan.stages.size() == 2) {
+    const Stage &sa = dp.plan.stages[0], &sb = dp.plan.stages[1];
+    fix.in = in; fix.out = out; fix.n_sig = n_sig;
+    fix.o0 = o0; fix.o1 = std::min<long>(o1, fi.n_head);
+    fix.gA = dp.stages[0].g.as<float>(); fix.gB = dp.stages[1].g.as<float>();
+    fix.nA = int(sa.g.size()); fix.nB = int(sb.g.size());
+    fix.LA = sa.L; fix.MA = sa.M; fix.LB = sb.L; fix.MB = sb.M;
+    fix.CA = sa.C; fix.CB = sb.C;
+    fix.n_u = 0; fix.m_min = fi.m_min;
+    fix_after = true;     // k_fdr below computes [o0, o1) including the head; the run-in terms are removed after it
+  } else if (o0 < fi.n_head) {
     // the first outputs, where the reference's intermediate signal starts at index 0 (cr.c:487-490)
     if (dp.plan.stages.size() != 2) return "internal: fdr head needs a two-stage plan";
     const Stage &sa = dp.plan.stages[0], &sb = dp.plan.stages[1];
@@ -337,6 +405,7 @@ const char *fdr_run(const DevicePlan &dp, const FdrInfo &fi, const SigDesc &in, 
     hp.LA = sa.L; hp.MA = sa.M; hp.LB = sb.L; hp.MB = sb.M;
     hp.CA = sa.C; hp.CB = sb.C;
     hp.n_u = fi.n_u;
+    hp.m_min = 0;
     if (fi.n_head <= 32)
       k_fdr_head_split<<<n_sig, 128, size_t(std::max(1, fi.n_u)) * sizeof(float), st>>>(hp);
     else
@@ -379,6 +448,15 @@ const char *fdr_run(const DevicePlan &dp, const FdrInfo &fi, const SigDesc &in, 
   P.itw2 = fi.itw.p;
   P.itw3 = static_cast<const char *>(fi.itw.p) + size_t(fi.itw3_off) * sizeof(float2);
   const long long n_items = (long long)P.n_pairs * P.n_blocks;
+  const char *err = launch_variant(fi, P, n_items, st);
+  if (err || !fix_after) return err;
+  k_fdr_head_fix<<<(n_sig + 3) / 4, 128, size_t(4) * size_t(-fi.m_min) * sizeof(float), st>>>(fix);
+  B2_COUNT_LAUNCH();
+  B2_CUDA(cudaGetLastError());
+  return nullptr;
+}
+
+static const char *launch_variant(const FdrInfo &fi, const FdrKParams &P, long long n_items, cudaStream_t st) {
   switch (fi.variant) {
     case 1: return launch_cfg<FdrCfg160_147>(fi, P, n_items, st);
     case 2: return launch_cfg<FdrCfg147_160>(fi, P, n_items, st);

@@ -299,6 +299,8 @@ struct FdrInfo {
   int adv_out = 0, adv_in = 0, m_in = 0, m_out = 0, nin = 0, nout = 0;
   size_t smem_bytes = 0;
   int n_u = 0;              // intermediate samples the head kernel needs
+  int m_min = 0;            // first (negative) intermediate index with a non-zero run-in value
+  bool head_by_fix = false; // long heads: k_fdr computes them like any output, k_fdr_head_fix removes the run-in terms
   DevBuf H, ftw, itw;       // response; forward / inverse twiddles (tw2 then tw3)
   int ftw3_off = 0, itw3_off = 0;
   ~FdrInfo() { H.release(); ftw.release(); itw.release(); }
@@ -324,6 +326,7 @@ struct FdrHeadParams {
   int nA, nB, LA, MA, LB, MB;
   long CA, CB;
   int n_u;                          // intermediate samples u[0 .. n_u) needed
+  int m_min;                        // k_fdr_head_fix: intermediate samples u[m_min .. 0) that the reference does not have
 };
 
 #ifdef __CUDACC__
