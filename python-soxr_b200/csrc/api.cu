@@ -106,8 +106,18 @@ struct b200soxr {
   const char *error = nullptr;
   std::vector<const void *> in_ptrs;
   std::vector<void *> out_ptrs;
+  // small host chunks (streaming): two mapped pinned staging buffers used alternately, each fenced by an event
+  // recorded behind the K1 launch that reads it, so a call that returns no output need not synchronise at all
+  PinnedBuf pin_in2[2];
+  cudaEvent_t in_ev[2] = {nullptr, nullptr};
+  bool in_ev_set[2] = {false, false};
+  int pin_toggle = 0;
 
   ~b200soxr() {
+    for (int i = 0; i < 2; ++i) {
+      if (in_ev[i]) { if (in_ev_set[i]) cudaEventSynchronize(in_ev[i]); cudaEventDestroy(in_ev[i]); }
+      pin_in2[i].release();
+    }
     xbuf.release();
     clips_dev.release();
     seed_dev.release();
@@ -319,6 +329,7 @@ b200soxr_error_t b200soxr_process(b200soxr_t p, void const *in, size_t ilen0, si
   Workspace *ws = p->ws;
   const char *e = nullptr;
 
+  int zc = -1;   // index of the mapped pinned staging buffer this call's input went through, if any
   // ---- input: H2D + deinterleave/convert into the device history (soxr.c:640-660)
   if (ilen && !p->emu->flushing()) {
     if ((e = p->grow_history(ilen))) return p->error = e;
@@ -336,10 +347,12 @@ b200soxr_error_t b200soxr_process(b200soxr_t p, void const *in, size_t ilen0, si
         // small chunk (streaming): no DMA at all.  The chunk is copied into pinned host memory that the device
         // maps at the same address (UVA) and K1 reads it over PCIe: one launch instead of a staged pageable
         // cudaMemcpy plus a launch.
-        if ((e = ws->pin_in.reserve(ilen * ch * isz))) return p->error = e;
-        std::memcpy(ws->pin_in.p, in, ilen * ch * isz);
+        zc = p->pin_toggle ^= 1;
+        if (p->in_ev_set[zc]) B2_CUDA(cudaEventSynchronize(p->in_ev[zc]));   // the K1 launch that last read this buffer
+        if ((e = p->pin_in2[zc].reserve(ilen * ch * isz))) return p->error = e;
+        std::memcpy(p->pin_in2[zc].p, in, ilen * ch * isz);
         lay.frame_stride = ch; lay.chan_stride = 1;
-        dev_in = ws->pin_in.p;
+        dev_in = p->pin_in2[zc].p;
       } else {
       if ((e = ws->in_stage.reserve(ilen * ch * isz))) return p->error = e;
       if (split) {
@@ -357,6 +370,11 @@ b200soxr_error_t b200soxr_process(b200soxr_t p, void const *in, size_t ilen0, si
     }
     if ((e = convert_in(lay, dev_in, ilen, p->dp->is_double, p->xbuf.p, p->x_cap, size_t(p->x_hi - p->x_base), st)))
       return p->error = e;
+    if (zc >= 0) {
+      if (!p->in_ev[zc]) B2_CUDA(cudaEventCreateWithFlags(&p->in_ev[zc], cudaEventDisableTiming));
+      B2_CUDA(cudaEventRecord(p->in_ev[zc], st));
+      p->in_ev_set[zc] = true;
+    }
     p->x_hi += long(ilen);
     p->emu->add_input(ilen);
   }
@@ -433,7 +451,8 @@ b200soxr_error_t b200soxr_process(b200soxr_t p, void const *in, size_t ilen0, si
       if (dith) p->seed = host[1];
     }
   }
-  if (!p->device_io) B2_CUDA(cudaStreamSynchronize(st));
+  // nothing to hand back and the input already consumed from the caller's buffer: leave the K1 launch queued
+  if (!p->device_io && !(zc >= 0 && odone == 0)) B2_CUDA(cudaStreamSynchronize(st));
   if (out_zero_copy && odone) std::memcpy(out, ws->pin_out.p, odone * ch * dtype_size(ot));
   p->out_done += long(odone);
   if (idone0) *idone0 = ilen;
