@@ -51,6 +51,11 @@ std::vector<float> make_twiddles(int *tw3_off) {
   return tw;
 }
 
+bool serial_head() {
+  static const bool v = [] { const char *e = std::getenv("B200SOXR_SERIAL_HEAD"); return e && e[0] == '1'; }();
+  return v;
+}
+
 bool fdr_disabled() {
   const char *env = std::getenv("B200SOXR_NO_FDR");
   if (env && env[0] == '1') return true;
@@ -375,10 +380,11 @@ const char *fdr_prepare(DevicePlan *dp) {
 static const char *launch_variant(const FdrInfo &fi, const FdrKParams &P, long long n_items, cudaStream_t st);
 
 const char *fdr_run(const DevicePlan &dp, const FdrInfo &fi, const SigDesc &in, const SigDesc &out, long o0, long o1,
-                    unsigned n_sig, unsigned group, cudaStream_t st) {
+                    unsigned n_sig, unsigned group, cudaStream_t st, Workspace *ws) {
   if (o1 <= o0 || !n_sig) return nullptr;
-  FdrHeadParams fix;
-  bool fix_after = false;
+  FdrHeadParams fix, head_params;
+  bool fix_after = false, head_after = false;
+  cudaStream_t head_stream = st;
   if (o0 < fi.n_head && fi.head_by_fix && dp.plan.stages.size() == 2) {
     const Stage &sa = dp.plan.stages[0], &sb = dp.plan.stages[1];
     fix.in = in; fix.out = out; fix.n_sig = n_sig;
@@ -406,12 +412,25 @@ const char *fdr_run(const DevicePlan &dp, const FdrInfo &fi, const SigDesc &in, 
     hp.CA = sa.C; hp.CB = sb.C;
     hp.n_u = fi.n_u;
     hp.m_min = 0;
-    if (fi.n_head <= 32)
-      k_fdr_head_split<<<n_sig, 128, size_t(std::max(1, fi.n_u)) * sizeof(float), st>>>(hp);
-    else
-      k_fdr_head<<<(n_sig + 3) / 4, 128, size_t(4) * size_t(std::max(1, fi.n_u)) * sizeof(float), st>>>(hp);
-    B2_COUNT_LAUNCH();
-    B2_CUDA(cudaGetLastError());
+    // The head kernel and k_fdr touch disjoint outputs.  When k_fdr follows, the head kernel goes to a side stream
+    // behind it: its blocks fill the SMs that k_fdr's persistent CTAs free at the end instead of adding their own
+    // pass (and tail) in front.
+    head_stream = st;
+    if (ws && o1 > fi.n_head && !serial_head()) {
+      if (const char *e = ws->need_aux()) return e;
+      B2_CUDA(cudaEventRecord(ws->aux_ev[0], st));
+      B2_CUDA(cudaStreamWaitEvent(ws->aux_stream, ws->aux_ev[0], 0));
+      head_stream = ws->aux_stream;
+      head_after = true;
+      head_params = hp;
+    } else {
+      if (fi.n_head <= 32)
+        k_fdr_head_split<<<n_sig, 128, size_t(std::max(1, fi.n_u)) * sizeof(float), st>>>(hp);
+      else
+        k_fdr_head<<<(n_sig + 3) / 4, 128, size_t(4) * size_t(std::max(1, fi.n_u)) * sizeof(float), st>>>(hp);
+      B2_COUNT_LAUNCH();
+      B2_CUDA(cudaGetLastError());
+    }
     o0 = fi.n_head;
     if (o1 <= o0) return nullptr;
   }
@@ -449,7 +468,18 @@ const char *fdr_run(const DevicePlan &dp, const FdrInfo &fi, const SigDesc &in, 
   P.itw3 = static_cast<const char *>(fi.itw.p) + size_t(fi.itw3_off) * sizeof(float2);
   const long long n_items = (long long)P.n_pairs * P.n_blocks;
   const char *err = launch_variant(fi, P, n_items, st);
-  if (err || !fix_after) return err;
+  if (err) return err;
+  if (head_after) {
+    if (fi.n_head <= 32)
+      k_fdr_head_split<<<n_sig, 128, size_t(std::max(1, fi.n_u)) * sizeof(float), head_stream>>>(head_params);
+    else
+      k_fdr_head<<<(n_sig + 3) / 4, 128, size_t(4) * size_t(std::max(1, fi.n_u)) * sizeof(float), head_stream>>>(head_params);
+    B2_COUNT_LAUNCH();
+    B2_CUDA(cudaGetLastError());
+    B2_CUDA(cudaEventRecord(ws->aux_ev[1], head_stream));
+    B2_CUDA(cudaStreamWaitEvent(st, ws->aux_ev[1], 0));
+  }
+  if (!fix_after) return nullptr;
   k_fdr_head_fix<<<(n_sig + 3) / 4, 128, size_t(4) * size_t(-fi.m_min) * sizeof(float), st>>>(fix);
   B2_COUNT_LAUNCH();
   B2_CUDA(cudaGetLastError());

@@ -577,6 +577,6 @@ std::vector<double> fdr_response(const Plan &plan, int rin, int rout, int nin, i
 const char *fdr_prepare(DevicePlan *dp);
 // final outputs [o0, o1) of all signals: k_fdr_head for [o0, n_head), k_fdr for the rest
 const char *fdr_run(const DevicePlan &dp, const FdrInfo &fi, const SigDesc &in, const SigDesc &out, long o0, long o1,
-                    unsigned n_sig, unsigned group, cudaStream_t st);
+                    unsigned n_sig, unsigned group, cudaStream_t st, Workspace *ws = nullptr);
 
 }  // namespace b2

@@ -59,6 +59,15 @@ Workspace::~Workspace() {
   if (d2h_stream) cudaStreamDestroy(d2h_stream);
   for (cudaEvent_t e : events) cudaEventDestroy(e);
   if (busy_ev) cudaEventDestroy(busy_ev);
+  if (aux_stream) cudaStreamDestroy(aux_stream);
+  for (cudaEvent_t e : aux_ev) if (e) cudaEventDestroy(e);
+}
+
+const char *Workspace::need_aux() {
+  if (!aux_stream) B2_CUDA(cudaStreamCreateWithFlags(&aux_stream, cudaStreamNonBlocking));
+  for (cudaEvent_t &e : aux_ev)
+    if (!e) B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return nullptr;
 }
 
 const char *Workspace::mark_busy(cudaStream_t st) {
@@ -410,7 +419,7 @@ const char *run_range_t(const DevicePlan &dp, const SigDesc &in0, long n_in_tota
       out0.dtype <= 1 && in0.base == 0) {
     // whole signals: single-pass frequency-domain kernel (the first few outputs, where the reference's
     // intermediate signal is cut at index 0, cr.c:487-490, come from its direct-form head kernel)
-    return fdr_run(dp, *dp.fdr, cur, out0, o0, o1, n_sig, group, st);
+    return fdr_run(dp, *dp.fdr, cur, out0, o0, o1, n_sig, group, st, ws);
   }
   if (S == 0)   // unity ratio: samples pass through (cr.c:347; zero-extended by flush)
     return sig_copy<T>(cur, out0, o0, o1, n_sig, st);

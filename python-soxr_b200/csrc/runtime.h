@@ -83,6 +83,10 @@ struct Workspace {
   const char *mark_busy(cudaStream_t st);
   DevBuf in_stage, out_stage, x, y, t0, t1, seeds, blocks, misc;
   PinnedBuf pin_in, pin_out, pin_misc;
+  // side stream for small kernels that may overlap the tail of a large one (k_fdr's head kernel), fenced by events
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t aux_ev[2] = {nullptr, nullptr};
+  const char *need_aux();
   ~Workspace();
 };
 // host_wait: block until queued work of the previous user has finished (callers that pass false
