@@ -10,12 +10,15 @@
 // transform, one REAL spectrum product (c is symmetric, the block grid keeps its centre on a
 // sample of both rates) and one inverse transform -- instead of the reference's FFT + spectrum
 // replication + larger inverse FFT (cr.c:87-146) followed by a 20-tap polyphase dot product per
-// output (poly-fir0.h:24-28).  The terms it drops are the images the reference folds back from
-// its own stop band (below -att dB); it is used for batches where att >= 150 dB (VHQ) so the
-// difference to the reference is ~1e-9 RMS, far inside the 1e-6 budget.  Blocks overlap by one
-// grid step (mr input / lr output samples) on each side, enough for the composite filter's
-// half-width; the first few outputs of a stream, where the reference's intermediate signal does
-// not exist before index 0 (cr.c:487-490), are recomputed by the exact direct-form kernels.
+// output (poly-fir0.h:24-28).  The terms it drops are the aliases a decimating cascade folds back
+// from its own stop band (below -att dB); it is used for whole-clip float32 arithmetic with
+// HQ/VHQ-class filters (att >= 132 dB: 2.8e-7 / 1.7e-7 RMS from the reference measured, budget
+// 1e-6) and for single 1/2 or 2/1 DFT stages at every quality, where the reference computes the
+// same thing (fdr_prepare in fdr_stage.cu has the rule).  Blocks overlap by a margin (OVL/2 grid
+// steps of mr input / lr output samples on each side) that covers the composite filter's
+// half-width; the first outputs of a clip, where the reference's intermediate signal does not
+// exist before index 0 (cr.c:487-490), come from the head kernels (fdr_stage.cu).  One FdrCfg per
+// ratio family (160:147, 147:160, 2:1, 1:2, 3:1, 1:3, 3:2, 2:3, 441:160, 6:1, 1:6, 4:1, 1:4).
 //
 // FFTs: N = RA*RB*RC, three register-radix passes (decimation in time forward, the mirrored
 // decimation in frequency backward) with shared-memory exchanges whose strides are chosen so
