@@ -114,3 +114,50 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "soxr_oracle" not in txt and "ref_soxr" not in txt and "libsoxr_ref" not in txt, f
+
+
+# ---- randomized, against the live reference (oracle/_ref, built by __graft_entry__.build() where the reference
+# sources exist): the planner and the integer call emulator over rates / chunkings the fixtures do not hold ---------
+def _ref_stream_counts(in_rate, out_rate, quality, lens):
+    import ref_soxr as R
+    rs = R.RefStream(in_rate, out_rate, 1, dtype='float32', quality=quality)
+    counts, delays = [], []
+    for n in lens:
+        y = rs.resample_chunk(np.zeros(n, np.float32), last=False)
+        counts.append(len(y))
+        delays.append(rs.delay())
+    return counts, delays
+
+
+def _ref_available():
+    try:
+        import ref_soxr as R
+        return R.available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(not _ref_available(), reason="oracle/_ref/libsoxr_ref.so not built")
+@pytest.mark.parametrize("seed", range(40))
+def test_call_emulation_matches_live_reference_on_random_partitions(seed):
+    rng = np.random.default_rng(1000 + seed)
+    rates = [8000, 11025, 16000, 22050, 24000, 32000, 44100, 48000, 88200, 96000, 47999, 44100.5]
+    in_rate, out_rate = (float(r) for r in rng.choice(rates, 2, replace=False))
+    quality = ['QQ', 'LQ', 'MQ', 'HQ', 'VHQ'][int(rng.integers(0, 5))]
+    lens = [int(v) for v in rng.integers(1, 3000, size=int(rng.integers(3, 25)))]
+    want_counts, want_delays = _ref_stream_counts(in_rate, out_rate, quality, lens)
+    got_counts, got_delays = soxr_ext.emulate_calls(in_rate, out_rate, Q[quality], lens)
+    assert got_counts == want_counts, (in_rate, out_rate, quality, lens)
+    assert np.allclose(got_delays, want_delays, rtol=0, atol=1e-9)
+
+
+@pytest.mark.skipif(not _ref_available(), reason="oracle/_ref/libsoxr_ref.so not built")
+@pytest.mark.parametrize("seed", range(24))
+def test_planner_matches_live_reference_trace_on_random_rates(seed):
+    import ref_soxr as R
+    rng = np.random.default_rng(2000 + seed)
+    in_rate = float(rng.integers(4000, 200000))
+    out_rate = float(rng.integers(4000, 200000)) + (0.5 if seed % 3 == 0 else 0.0)
+    quality = ['LQ', 'MQ', 'HQ', 'VHQ'][seed % 4]
+    want = [l for l in R.trace_plan(in_rate, out_rate, quality) if l.startswith('fir_len') or '>>' in l]
+    assert soxr_ext.plan_dump(in_rate, out_rate, Q[quality]) == want, (in_rate, out_rate, quality)
