@@ -98,3 +98,22 @@ def test_oracle_matches_reference_live(case):
     y = O.resample_f64(x, ir, orate, Q[q])
     assert y.shape == y_ref.shape
     assert rms(y - y_ref) <= TOL_F64_ENGINE
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref/libsoxr_ref.so not built")
+@pytest.mark.parametrize("seed", range(16))
+def test_oracle_matches_reference_live_on_random_rates(seed):
+    # the oracle's closed form against the reference's f64 engine (VHQ) at rates the fixtures do not hold,
+    # rational and irrational, up and down
+    rng = np.random.default_rng(3000 + seed)
+    rates = [8000, 11025, 12000, 16000, 22050, 24000, 32000, 44100, 48000, 88200, 96000]
+    ir = float(rng.choice(rates))
+    orate = float(rng.choice(rates)) + (0.5 if seed % 4 == 0 else 0.0)
+    if ir == orate:
+        orate = ir * 1.5
+    n = int(rng.integers(1, 4000))
+    x = rng.standard_normal((n, 1))
+    y_ref = R.divide_proc(ir, orate, x, 'VHQ')
+    y = O.resample_f64(x, ir, orate, O.VHQ)
+    assert y.shape == y_ref.shape, (ir, orate, n)
+    assert rms(y - y_ref) <= TOL_F64_ENGINE, (ir, orate, n)
