@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -28,13 +29,14 @@ namespace {
 const char *kNoDevice = "b200soxr: no usable CUDA device (this library has no CPU fallback)";
 
 bool device_ok() {
-  static int state = -1;
-  if (state < 0) {
+  static std::once_flag once;
+  static bool ok = false;
+  std::call_once(once, [] {
     int n = 0;
-    state = (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) ? 1 : 0;
-    if (!state) cudaGetLastError();
-  }
-  return state == 1;
+    ok = cudaGetDeviceCount(&n) == cudaSuccess && n > 0;
+    if (!ok) cudaGetLastError();
+  });
+  return ok;
 }
 
 QSpec to_qspec(const b200soxr_quality_spec_t &q) {
@@ -87,6 +89,7 @@ size_t div_len_of(double in_rate, double out_rate) {          // soxr_ext.cpp:71
 // stream handle
 // ---------------------------------------------------------------------------
 struct b200soxr {
+  int device = -1;        // the CUDA device this handle's plan, stream and buffers live on
   unsigned channels = 0;
   double io_ratio = 0;
   b200soxr_io_spec_t io{};
@@ -114,6 +117,7 @@ struct b200soxr {
   int pin_toggle = 0;
 
   ~b200soxr() {
+    DeviceGuard guard(device);
     for (int i = 0; i < 2; ++i) {
       if (in_ev[i]) { if (in_ev_set[i]) cudaEventSynchronize(in_ev[i]); cudaEventDestroy(in_ev[i]); }
       pin_in2[i].release();
@@ -257,6 +261,7 @@ b200soxr_t b200soxr_create(double input_rate, double output_rate, unsigned num_c
   else if (!device_ok()) error = kNoDevice;
   if (!error && !(p = new (std::nothrow) b200soxr())) error = "malloc failed";
   if (p) {
+    if (cudaGetDevice(&p->device) != cudaSuccess) { cudaGetLastError(); p->device = 0; }
     p->channels = num_channels;
     p->io_ratio = io_ratio;
     if (io_spec) p->io = *io_spec;
@@ -292,15 +297,19 @@ char const *b200soxr_engine(b200soxr_t p) { return p->dp->is_double ? "b200-cr64
 
 b200soxr_error_t b200soxr_clear(b200soxr_t p) {
   if (!p) return "invalid soxr_t pointer";
+  DeviceGuard guard(p->device);
   // The reference rebuilds the resampler and zeroes everything else, incl. the
   // clip counter and the dither seed (soxr.c:609-628).
   p->clips = 0;
   p->seed = 0;
   p->error = nullptr;
+  // the device-side accumulators k_rint_clip / k_dither_seeds add to restart as well
+  if (p->clips_dev.p) B2_CUDA(cudaMemsetAsync(p->clips_dev.p, 0, 8, p->stream));
+  if (p->seed_dev.p) B2_CUDA(cudaMemsetAsync(p->seed_dev.p, 0, 8, p->stream));
   return p->init_state();
 }
 
-void b200soxr_delete(b200soxr_t p) { delete p; }
+void b200soxr_delete(b200soxr_t p) { delete p; }   // ~b200soxr switches to the handle's device itself
 
 // host chunks / results up to this size bypass the copy engines (see b200soxr_process)
 static const size_t kZeroCopyBytes = [] {
@@ -312,6 +321,7 @@ b200soxr_error_t b200soxr_process(b200soxr_t p, void const *in, size_t ilen0, si
                                   size_t olen, size_t *odone0) {
   if (!p) return "null pointer";
   if (p->error) return p->error;
+  DeviceGuard guard(p->device);
   size_t ilen;
   bool flush_requested = false;
   if (!in) { flush_requested = true; ilen = ilen0 = 0; }
@@ -488,14 +498,14 @@ b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *d, void co
   if (d->dtype < 0 || d->dtype > 3) return "invalid io datatype(s)";
   if (!d->channels || !d->n_clips) return "invalid # of channels";
   if (!device_ok()) return kNoDevice;
+  int run_device = -1;
   if ((d->flags & B200SOXR_BATCH_DEVICE_PTRS) && in) {
     // run on the device that owns the buffers (one process may drive several GPUs)
     cudaPointerAttributes pa;
-    if (cudaPointerGetAttributes(&pa, in) == cudaSuccess && pa.type == cudaMemoryTypeDevice) {
-      int cur = -1;
-      if (cudaGetDevice(&cur) == cudaSuccess && cur != pa.device) B2_CUDA(cudaSetDevice(pa.device));
-    } else cudaGetLastError();
+    if (cudaPointerGetAttributes(&pa, in) == cudaSuccess && pa.type == cudaMemoryTypeDevice) run_device = pa.device;
+    else cudaGetLastError();
   }
+  DeviceGuard guard(run_device);   // the caller's current device is restored on return
   const double io_ratio = d->in_rate / d->out_rate;
   const QSpec q = quality_spec(d->quality, (d->flags & B200SOXR_BATCH_DOUBLE) ? B200SOXR_DOUBLE_PRECISION : 0);
   std::shared_ptr<DevicePlan> dp;

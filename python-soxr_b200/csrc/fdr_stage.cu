@@ -6,7 +6,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <mutex>
 #include <numeric>
+#include <vector>
 
 namespace b2 {
 
@@ -309,35 +311,46 @@ const char *prepare_cfg(DevicePlan *dp, int variant) {
   return nullptr;
 }
 
-template <class Cfg>
-const char *launch_cfg(const FdrInfo &fi, const FdrKParams &P, long long n_items, cudaStream_t st) {
-  auto kern = k_fdr<Cfg>;
+template <class Cfg, bool FAST>
+const char *launch_cfg_t(const FdrInfo &fi, const FdrKParams &P, long long n_items, cudaStream_t st) {
+  auto kern = k_fdr<Cfg, FAST>;
   int dev = 0;
   cudaGetDevice(&dev);
-  static bool attr_set[16] = {};   // per instantiation (one set of statics per Cfg)
-  static int per_sm[16] = {};
-  static int sm_count[16] = {};
-  const int di = dev & 15;
+  // per instantiation (one set of statics per Cfg and FAST) and per device, initialised once under a mutex:
+  // concurrent callers (the reference's thread-pool tests) launch from many threads
+  struct DevCfg { bool set = false; int per_sm = 1, sm_count = 148; };
+  static std::mutex mu;
+  static std::vector<DevCfg> cfgs;
   // B200SOXR_FDR_PAD_KB: extra dynamic shared memory per CTA, to study throughput against CTAs per SM
   static const size_t pad = [] { const char *v = std::getenv("B200SOXR_FDR_PAD_KB"); return v ? size_t(std::atol(v)) << 10 : size_t(0); }();
   const size_t smem_bytes = fi.smem_bytes + pad;
-  if (!attr_set[di]) {
-    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[di], kern, Cfg::THREADS, smem_bytes) != cudaSuccess ||
-        per_sm[di] < 1) {
-      cudaGetLastError();
-      per_sm[di] = 1;
+  DevCfg dc;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (cfgs.size() <= size_t(dev)) cfgs.resize(size_t(dev) + 1);
+    DevCfg &c = cfgs[size_t(dev)];
+    if (!c.set) {
+      B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
+      cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.per_sm, kern, Cfg::THREADS, smem_bytes) != cudaSuccess || c.per_sm < 1) {
+        cudaGetLastError();
+        c.per_sm = 1;
+      }
+      if (cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || c.sm_count < 1)
+        c.sm_count = 148;
+      c.set = true;
     }
-    if (cudaDeviceGetAttribute(&sm_count[di], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count[di] < 1)
-      sm_count[di] = 148;
-    attr_set[di] = true;
+    dc = c;
   }
-  const long long grid = std::min<long long>(n_items, (long long)sm_count[di] * per_sm[di]);
+  const long long grid = std::min<long long>(n_items, (long long)dc.sm_count * dc.per_sm);
   kern<<<unsigned(grid), Cfg::THREADS, smem_bytes, st>>>(P);
   B2_COUNT_LAUNCH();
   B2_CUDA(cudaGetLastError());
   return nullptr;
+}
+template <class Cfg>
+const char *launch_cfg(const FdrInfo &fi, const FdrKParams &P, long long n_items, cudaStream_t st) {
+  return P.fast ? launch_cfg_t<Cfg, true>(fi, P, n_items, st) : launch_cfg_t<Cfg, false>(fi, P, n_items, st);
 }
 }  // namespace
 

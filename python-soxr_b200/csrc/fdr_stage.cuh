@@ -224,7 +224,11 @@ struct Fft3 {
 
 constexpr int fdr_cmax(int a, int b) { return a > b ? a : b; }
 // threads (a multiple of 32) taking part in a pass over G items done in ceil(G / threads) rounds
+#ifndef B2_FDR_TP_GREEDY
+#define B2_FDR_TP_GREEDY 0
+#endif
 constexpr int fdr_tp(int G, int threads) {
+  if (B2_FDR_TP_GREEDY && G > threads) return threads;   // every warp in the first round, the remainder in a short second one
   const int rounds = (G + threads - 1) / threads;
   const int per = (G + rounds - 1) / rounds;
   return (per + 31) / 32 * 32;
@@ -333,7 +337,10 @@ struct FdrHeadParams {
 };
 
 #ifdef __CUDACC__
-template <class Cfg>
+// FAST: every pair is interleaved stereo float32 on both sides (FdrKParams::fast, checked on the host) -- a separate
+// instantiation, so the other layouts (block-paired mono, strided, integer) cost the headline path neither
+// registers nor predicates.
+template <class Cfg, bool FAST>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKParams P) {
   typedef float R;
   typedef float2 C;
@@ -358,6 +365,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
   // Per-pair state kept in registers across blocks: only what the interleaved-stereo fast path needs.  The other
   // layouts recompute their address set-up (pair_state) where they use it: at 64 registers per thread the full
   // state lived in local memory, and its reloads were 5 % of the warp stall samples (profiles/r1v).
+  constexpr bool fast = FAST;
+  const bool bpair = !FAST && P.bpair != 0;
   struct PairState {
     PairIn<R> pin;
     long long ooff0, ooff1;
@@ -366,8 +375,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
   auto pair_state = [&](unsigned pr) {
     PairState ps;
     const unsigned clip = pr / P.ppg, cp = pr % P.ppg;
-    const unsigned s0 = P.bpair ? pr : clip * P.group + 2 * cp, s1 = s0 + 1;
-    ps.has1 = !P.bpair && 2 * cp + 1 < P.group;
+    const unsigned s0 = bpair ? pr : clip * P.group + 2 * cp, s1 = s0 + 1;
+    ps.has1 = !bpair && 2 * cp + 1 < P.group;
     ps.pin = make_pair_in<R>(P.in, s0, ps.has1);
     ps.ooff0 = (long long)(s0 / P.out.channels) * P.out.clip_stride + (long long)(s0 % P.out.channels) * P.out.chan_stride -
                P.out.base * P.out.frame_stride;
@@ -378,7 +387,6 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
               !(reinterpret_cast<unsigned long long>(P.out.p) & 7);
     return ps;
   };
-  const bool fast = P.fast != 0;   // launch-uniform, lives in the constant bank
   const float2 *src_pair = nullptr;
   float2 *dst_pair = nullptr;
 
@@ -402,7 +410,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
       dst_pair = reinterpret_cast<float2 *>(static_cast<float *>(P.out.p) + ps.ooff0);
       fresh = false;
     }
-    const long b = P.b_first + (P.bpair ? 2 * bi : bi);
+    const long b = P.b_first + (bpair ? 2 * bi : bi);
     const long kb = b * long(Cfg::ADV_IN) - Cfg::M_IN;      // input index of block point 0
     const long nb = b * long(Cfg::ADV_OUT) - Cfg::M_OUT;    // output index of block point 0
     const bool interior = kb >= P.in.vlo && kb + Cfg::NIN <= P.in.vhi;
@@ -415,7 +423,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
       FW::template fwd_p1<Cfg::TP_F1>(tau, bufA, [&](int g, int n) { return stg[FW::S1 * n + g]; });
     } else
 #endif
-    if (P.bpair) {
+    if (bpair) {
       // one signal, two consecutive blocks: block b in the real part, block b + 1 in the imaginary part
       const PairIn<R> pin = pair_state(pair).pin;
       const bool both_in = interior && kb + Cfg::ADV_IN + Cfg::NIN <= pin.vhi && pin.fs == 1;
@@ -488,7 +496,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
       // bufB's last readers (the second inverse pass) are all past the barrier above; it becomes the next
       // block's bufA.  Same pair, whole block inside the clip, 16-byte aligned rows: else the next block loads itself.
       const long kn = kb + Cfg::ADV_IN;
-      staged = fast && !P.bpair && it + 1 < n_mine && bi + 1 < P.n_blocks && kn >= P.in.vlo && kn + Cfg::NIN <= P.in.vhi &&
+      staged = fast && !bpair && it + 1 < n_mine && bi + 1 < P.n_blocks && kn >= P.in.vlo && kn + Cfg::NIN <= P.in.vhi &&
                !(reinterpret_cast<unsigned long long>(src_pair + kn) & 15);
       if (staged && tau == 0) {
         static_assert(FW::S1 % 2 == 0 && FW::G1 % 2 == 0 && Cfg::BUF_A % 2 == 0, "16-byte rows for the bulk copies");
@@ -503,7 +511,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
     {
       // owned outputs: block-local o in [M_OUT, M_OUT + ADV_OUT), clipped to the requested range
       const int lo = int(max(long(Cfg::M_OUT), P.o0 - nb)), hi = int(min(long(Cfg::M_OUT + Cfg::ADV_OUT), P.o1 - nb));
-      if (P.bpair) {
+      if (bpair) {
         const long long ooff0 = pair_state(pair).ooff0;
         const long nb1 = nb + Cfg::ADV_OUT;                  // block b + 1 (imaginary part)
         const int lo1 = int(max(long(Cfg::M_OUT), P.o0 - nb1)), hi1 = int(min(long(Cfg::M_OUT + Cfg::ADV_OUT), P.o1 - nb1));

@@ -55,14 +55,15 @@ __host__ __device__ __forceinline__ float2 csub(float2 a, float2 b) {
 __host__ __device__ __forceinline__ float2 rot(float2 a) { return make_float2(a.y, -a.x); }
 __host__ __device__ __forceinline__ float2 axpy(float s, float2 b, float2 a) {
 #if B2_PACKED_F32
-  return __ffma2_rn(make_float2(s, s), b, a);
+  return __ffma2_rn(b, make_float2(s, s), a);   // swizzled pair (rot) in the A slot, broadcast scalar in B: ptxas folds
+                                                  // LO_HI.NP only on A (else it materialises the negation: FADD + MOV)
 #else
   return make_float2(fmaf(s, b.x, a.x), fmaf(s, b.y, a.y));
 #endif
 }
 __host__ __device__ __forceinline__ float2 scale(float s, float2 a) {
 #if B2_PACKED_F32
-  return __fmul2_rn(make_float2(s, s), a);
+  return __fmul2_rn(a, make_float2(s, s));
 #else
   return make_float2(s * a.x, s * a.y);
 #endif

@@ -85,6 +85,18 @@ __global__ void k_rational(SigIn<T> in, const T *__restrict__ g, int n_g, long C
   }
 }
 
+// 32.32 fixed-point stage clock at absolute output index n: at0 + step * n evaluated in 96 bits (64-bit integer
+// part, 32-bit fraction), so a stream can run past 2^32 stage-input samples.  The reference carries the same
+// clock incrementally and rebases its integer part every call (poly-fir.h:74-86); the values agree exactly.
+__device__ __forceinline__ void clock_at(unsigned long long at0, unsigned long long step, unsigned long long n,
+                                         long long *whole, unsigned *frac) {
+  const unsigned long long lo = step * n, hi = __umul64hi(step, n);
+  const unsigned long long sum = lo + at0;
+  const unsigned long long carry = sum < lo ? 1ull : 0ull;
+  *whole = (long long)(((hi + carry) << 32) | (sum >> 32));
+  *frac = unsigned(sum);
+}
+
 // ---- interpolated-coefficient polyphase stage (vpoly1..3, poly-fir.h:89-101):
 // 32.32 fixed-point clock; phase = top `phase_bits` of the fraction, x = the rest.
 // table: [phase][tap][order+1], highest order first.
@@ -102,9 +114,10 @@ __global__ void k_poly_interp(SigIn<T> in, const T *__restrict__ table, int n_ta
   const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n_out) return;
   const long n = o0 + i;
-  const unsigned long long at = at0 + step * (unsigned long long)n;
-  const long pos = long(at >> 32) - preload;
-  const unsigned frac = unsigned(at);
+  long long whole;
+  unsigned frac;
+  clock_at(at0, step, (unsigned long long)n, &whole, &frac);
+  const long pos = long(whole) - preload;
   const int phase = int(frac >> (32 - phase_bits));
   const T x = T(double(unsigned(frac << phase_bits)) * (1. / 4294967296.));
   const T *c = table + size_t(phase) * n_taps * (order + 1);
@@ -129,9 +142,11 @@ __global__ void k_cubic(SigIn<T> in, unsigned long long step, double mult, SigOu
   const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n_out) return;
   const long n = o0 + i;
-  const unsigned long long at = step * (unsigned long long)n;
-  const long p = long(at >> 32);
-  const double x = double(unsigned(at)) * (1. / 4294967296.);
+  long long whole;
+  unsigned frac;
+  clock_at(0ull, step, (unsigned long long)n, &whole, &frac);
+  const long p = long(whole);
+  const double x = double(frac) * (1. / 4294967296.);
   for (unsigned s = blockIdx.y; s < n_sig; s += gridDim.y) {
     const double s0 = in.at(s, p), s1 = in.at(s, p + 1), s2 = in.at(s, p + 2), sm = in.at(s, p - 1);
     const double b = .5 * (s1 + sm) - s0, a = (1 / 6.) * (s2 - s1 + sm - s0 - 4 * b), c = s1 - s0 - a - b;

@@ -411,6 +411,12 @@ const char *make_plan(double io_ratio, const QSpec &q, const RSpec &r, double mu
 
 // ---------------------------------------------------------------------------
 
+// integer part of the 32.32 stage clock at0 + step * n, in 96 bits (see clock_at in kernels_generic.cuh)
+static long clock_whole(uint64_t at0, uint64_t step, long n) {
+  const unsigned __int128 at = (unsigned __int128)step * (unsigned __int128)(uint64_t)n + at0;
+  return long((unsigned long long)(at >> 32));
+}
+
 long stage_input_first(const Stage &s, long n) {
   switch (s.kind) {
     case kHalf: case kDft: case kPoly: {
@@ -419,8 +425,8 @@ long stage_input_first(const Stage &s, long n) {
       const long top = s.C + long(s.M) * n, t = top - (long(s.g.size()) - 1);
       return t >= 0 ? (t + s.L - 1) / s.L : -((-t) / s.L);
     }
-    case kPolyInterp: return long((s.at0_fix + s.step_fix * uint64_t(n)) >> 32) - s.dev_preload;
-    case kCubic: return long((s.step_fix * uint64_t(n)) >> 32) - 1;
+    case kPolyInterp: return clock_whole(s.at0_fix, s.step_fix, n) - s.dev_preload;
+    case kCubic: return clock_whole(0, s.step_fix, n) - 1;
   }
   return 0;
 }
@@ -433,8 +439,8 @@ long stage_input_needed(const Stage &s, long n_out) {
       return top < 0 ? 0 : top / s.L + 1;
     }
     case kPolyInterp:
-      return std::max(0L, long((s.at0_fix + s.step_fix * uint64_t(n_out - 1)) >> 32) + s.num_coefs - s.dev_preload);
-    case kCubic: return long((s.step_fix * uint64_t(n_out - 1)) >> 32) + 3;
+      return std::max(0L, clock_whole(s.at0_fix, s.step_fix, n_out - 1) + s.num_coefs - s.dev_preload);
+    case kCubic: return clock_whole(0, s.step_fix, n_out - 1) + 3;
   }
   return 0;
 }

@@ -22,6 +22,20 @@ const char *cuda_err(cudaError_t e);   // static string for the error
     if (e__ != cudaSuccess) return ::b2::cuda_err(e__); \
   } while (0)
 
+// Makes `device` current for the calling thread and restores the previous one on scope exit, so an entry point
+// never changes the caller's current device (torch and other libraries rely on it).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int device) {
+    if (device >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != device)
+      switched = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard &) = delete;
+  DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+
 // Growable device buffer (never shrinks; freed with its owner).
 struct DevBuf {
   void *p = nullptr;
