@@ -515,7 +515,6 @@ b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *d, void co
   if (clips) *clips = 0;
   if (total > d->olen) return "b200soxr: output buffer too small";
   const bool dev_ptrs = d->flags & B200SOXR_BATCH_DEVICE_PTRS;
-  const unsigned n_sig = d->n_clips * d->channels;
   const size_t esz = dp->is_double ? 8 : 4, isz = dtype_size(d->dtype);
 
   Workspace *ws = acquire_workspace(false);

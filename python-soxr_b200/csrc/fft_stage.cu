@@ -7,6 +7,8 @@
 #include <algorithm>
 #include <complex>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 namespace b2 {
 
@@ -118,22 +120,35 @@ const char *prepare_t(DevicePlan *dp, FftStageInfo &fi) {
 template <typename R, int LOG2N, int L, int M, bool POLY>
 const char *launch(const FftStageInfo &fi, const FftKParams &P, long long n_items, cudaStream_t st) {
   auto kern = k_fft_stage<R, LOG2N, L, M, POLY>;
-  static size_t attr_smem[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int dev = 0;
   cudaGetDevice(&dev);
   constexpr int G = FftCta<R, LOG2N>::G, THREADS = FftCta<R, LOG2N>::THREADS;
   const size_t smem = smem_for(fi, sizeof(R), G);
-  if (dev >= 8 || attr_smem[dev] < smem) {   // opt in to > 48 kB of dynamic shared memory
-    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    if (dev < 8) attr_smem[dev] = smem;
-  }
-  static int sm_count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (dev < 8 && !sm_count[dev]) cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
-  const int sms = dev < 8 && sm_count[dev] ? sm_count[dev] : 148;
-  int per_sm = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem) != cudaSuccess || per_sm < 1) {
-    cudaGetLastError();
-    per_sm = 1;
+  // per instantiation and device, under a mutex: many host threads launch concurrently (the reference's
+  // thread-pool tests).  The dynamic shared-memory opt-in only ever grows; occupancy is cached per size.
+  struct DevCfg { size_t attr_smem = 0, occ_smem = ~size_t(0); int per_sm = 1, sm_count = 0; };
+  static std::mutex mu;
+  static std::vector<DevCfg> cfgs;
+  int sms, per_sm;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (cfgs.size() <= size_t(dev)) cfgs.resize(size_t(dev) + 1);
+    DevCfg &c = cfgs[size_t(dev)];
+    if (c.attr_smem < smem) {   // opt in to > 48 kB of dynamic shared memory
+      B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      c.attr_smem = smem;
+    }
+    if (!c.sm_count && (cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || c.sm_count < 1))
+      c.sm_count = 148;
+    if (c.occ_smem != smem) {
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.per_sm, kern, THREADS, smem) != cudaSuccess || c.per_sm < 1) {
+        cudaGetLastError();
+        c.per_sm = 1;
+      }
+      c.occ_smem = smem;
+    }
+    sms = c.sm_count;
+    per_sm = c.per_sm;
   }
   const long long grid = std::min<long long>((n_items + G - 1) / G, (long long)sms * per_sm);
   kern<<<unsigned(grid), THREADS, smem, st>>>(P);

@@ -110,8 +110,13 @@ struct PlanKey {
   int device, arith_double;
   bool operator<(const PlanKey &o) const { return std::memcmp(this, &o, sizeof *this) < 0; }
 };
+// Bounded (least recently used entry dropped): a long-running process that sweeps ratios must not grow device
+// memory without limit.  Handles keep their plan alive through the shared_ptr.
+struct PlanEntry { std::shared_ptr<DevicePlan> dp; unsigned long long last_use = 0; };
+constexpr size_t kMaxCachedPlans = 64;
 std::mutex g_plan_mu;
-std::map<PlanKey, std::shared_ptr<DevicePlan>> g_plans;
+std::map<PlanKey, PlanEntry> g_plans;
+unsigned long long g_plan_tick = 0;
 }  // namespace
 
 Workspace *acquire_workspace(bool host_wait) {
@@ -166,7 +171,7 @@ const char *get_device_plan(double io_ratio, const QSpec &q, const RSpec &r, dou
   key.arith_double = arith_double ? 1 : 0;
   std::lock_guard<std::mutex> l(g_plan_mu);
   auto it = g_plans.find(key);
-  if (it != g_plans.end()) { *out = it->second; return nullptr; }
+  if (it != g_plans.end()) { it->second.last_use = ++g_plan_tick; *out = it->second.dp; return nullptr; }
   auto dp = std::make_shared<DevicePlan>();
   if (const char *e = make_plan(io_ratio, q, r, multiplier, &dp->plan)) return e;
   dp->is_double = arith_double;
@@ -186,7 +191,13 @@ const char *get_device_plan(double io_ratio, const QSpec &q, const RSpec &r, dou
   }
   if (const char *e = fft_stage_prepare(dp.get())) return e;
   if (const char *e = fdr_prepare(dp.get())) return e;
-  g_plans[key] = dp;
+  if (g_plans.size() >= kMaxCachedPlans) {
+    auto victim = g_plans.begin();
+    for (auto j = g_plans.begin(); j != g_plans.end(); ++j)
+      if (j->second.last_use < victim->second.last_use) victim = j;
+    g_plans.erase(victim);
+  }
+  g_plans[key] = PlanEntry{dp, ++g_plan_tick};
   *out = dp;
   return nullptr;
 }

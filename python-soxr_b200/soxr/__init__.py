@@ -139,18 +139,38 @@ def _resample_oneshot(x, in_rate, out_rate, quality='HQ'):
     return oneshot(in_rate, out_rate, x, q)
 
 
+def _check_batch_out(out, shape, dtype, like=None):
+    """A caller-supplied `out` is written through raw pointers: it must be exactly what the call would allocate."""
+    if tuple(out.shape) != tuple(shape):
+        raise ValueError('out has shape {}, expected {}'.format(tuple(out.shape), tuple(shape)))
+    if out.dtype != dtype:
+        raise ValueError('out has dtype {}, expected {}'.format(out.dtype, dtype))
+    if like is None:
+        if type(out) != np.ndarray or not out.flags.c_contiguous or not out.flags.writeable:
+            raise ValueError('out must be a writeable C-contiguous numpy.ndarray')
+    else:
+        if not out.is_cuda or out.device != like.device:
+            raise ValueError('out must be a CUDA tensor on the same device as the input ({})'.format(like.device))
+        if not out.is_contiguous():
+            raise ValueError('out must be contiguous')
+
+
 def resample_batch(x, in_rate, out_rate, quality='HQ', out=None, stream=None, exact_grid=False):
     """B200 extension: resample a batch of equal-length clips in one go.
 
     x: [clip, frame] (mono clips) or [clip, frame, channel], C-contiguous;
     a numpy array (host; copies included) or a torch CUDA tensor (device
-    resident; asynchronous on `stream` or torch's current stream).
+    resident; asynchronous on `stream` -- an integer cudaStream_t handle -- or
+    torch's current stream).  `out`, if given, must have exactly the shape,
+    dtype, device and C-contiguous layout the call would allocate.
     Returns the same kind of container with floor(frames*out/in + .5) frames.
 
-    exact_grid=True keeps the reference's block grid (results bit-identical to a
-    ResampleStream fed the same clip); by default whole-clip float32 VHQ work at
-    48000:44100-type ratios runs through the single-pass frequency-domain kernel,
-    which agrees with it to ~2e-7 RMS (float32 rounding).
+    exact_grid=True keeps the reference's block grid: every clip is then
+    bit-identical to `soxr.resample` / a ResampleStream on that clip (int16
+    included: the dither replays the per-clip call partition either way).  By
+    default whole-clip float32 arithmetic at the ratio families of the
+    single-pass frequency-domain kernel (48000:44100, 2:1, 3:1, ...) runs through
+    that kernel, which agrees with the exact grid to ~2e-7 RMS (float32 rounding).
     """
     _check_rates(in_rate, out_rate)
     q = _quality_to_enum(quality)
@@ -158,32 +178,47 @@ def resample_batch(x, in_rate, out_rate, quality='HQ', out=None, stream=None, ex
     ndim = x.ndim
     if ndim not in (2, 3):
         raise ValueError('Input must be [clip, frame] or [clip, frame, channel]')
+    if stream is not None and (isinstance(stream, bool) or not isinstance(stream, (int, np.integer))):
+        raise TypeError('stream must be an integer cudaStream_t handle (e.g. torch.cuda.Stream.cuda_stream)')
     n_clips, ilen = int(x.shape[0]), int(x.shape[1])
     ch = int(x.shape[2]) if ndim == 3 else 1
     _check_channels(ch)
     total = soxr_ext.output_frames(in_rate, out_rate, ilen)
+    shape = (n_clips, total, ch) if ndim == 3 else (n_clips, total)
+    if n_clips == 0:
+        if out is not None:
+            _check_batch_out(out, shape, x.dtype, like=x if is_torch else None)
+            return out
+        if is_torch:
+            import torch
+            return torch.empty(shape, dtype=x.dtype, device=x.device)
+        return np.empty(shape, dtype=x.dtype)
+    # int16 dither replays the call partition `soxr.resample` would make for each clip (soxr_ext.cpp:239-257)
+    flags = soxr_ext.BATCH_EMULATE_CALLS | (soxr_ext.BATCH_EXACT_GRID if exact_grid else 0)
     if is_torch:
         import torch
         if not x.is_cuda:
             raise ValueError('torch input must be a CUDA tensor (use numpy for host data)')
         x = x.contiguous()
         code = _to_soxr_datatype(str(x.dtype).replace('torch.', ''))
-        shape = (n_clips, total, ch) if ndim == 3 else (n_clips, total)
         if out is None:
             out = torch.empty(shape, dtype=x.dtype, device=x.device)
-        s = stream if stream is not None else torch.cuda.current_stream(x.device).cuda_stream
+        else:
+            _check_batch_out(out, shape, x.dtype, like=x)
+        s = int(stream) if stream is not None else torch.cuda.current_stream(x.device).cuda_stream
         soxr_ext.resample_batch_raw(x.data_ptr(), out.data_ptr(), in_rate=in_rate, out_rate=out_rate, quality=q,
                                     dtype_code=code, n_clips=n_clips, channels=ch, ilen=ilen,
                                     in_strides=(ilen * ch, ch, 1), out_strides=(total * ch, ch, 1), olen=total,
-                                    flags=soxr_ext.BATCH_DEVICE_PTRS | (soxr_ext.BATCH_EXACT_GRID if exact_grid else 0), stream=s)
+                                    flags=soxr_ext.BATCH_DEVICE_PTRS | flags, stream=s)
         return out
     x = np.ascontiguousarray(x)
     code = _to_soxr_datatype(x.dtype)
-    shape = (n_clips, total, ch) if ndim == 3 else (n_clips, total)
     if out is None:
         out = np.empty(shape, dtype=x.dtype)
+    else:
+        _check_batch_out(out, shape, x.dtype)
     soxr_ext.resample_batch_raw(x.ctypes.data, out.ctypes.data, in_rate=in_rate, out_rate=out_rate, quality=q,
                                 dtype_code=code, n_clips=n_clips, channels=ch, ilen=ilen,
                                 in_strides=(ilen * ch, ch, 1), out_strides=(total * ch, ch, 1), olen=total,
-                                flags=soxr_ext.BATCH_EXACT_GRID if exact_grid else 0)
+                                flags=flags, stream=None if stream is None else int(stream))
     return out

@@ -28,7 +28,11 @@ _SPLIT = 4
 
 BATCH_DEVICE_PTRS, BATCH_NO_DITHER, BATCH_DOUBLE = 1, 2, 4
 BATCH_EMULATE_CALLS, BATCH_ONESHOT_CALLS, BATCH_SPLIT_SEMANTICS = 8, 16, 32
-BATCH_EXACT_GRID = 64   # reference block grid only: bit-identical to a ResampleStream fed the same input
+# Reference block grid only: bit-identical to a ResampleStream fed the same input.  The three whole-signal drivers
+# below (divide_proc, split_ch, oneshot) always set it, so `resample == _resample_oneshot == ResampleStream`
+# holds bit for bit at every ratio like in the reference (tests/test_resample.py:46-116); the faster single-pass
+# frequency-domain kernel is what `soxr.resample_batch` / b200soxr_resample_batch use by default.
+BATCH_EXACT_GRID = 64
 RT_DEVICE_IO = 0x100
 
 
@@ -298,7 +302,7 @@ def _make_divide_proc(code):
         resample_batch_raw(x.ctypes.data, y.ctypes.data, in_rate=in_rate, out_rate=out_rate, quality=int(quality),
                            dtype_code=code, n_clips=1, channels=ch, ilen=ilen,
                            in_strides=(0, ch, 1), out_strides=(0, ch, 1), olen=total,
-                           flags=BATCH_EMULATE_CALLS)
+                           flags=BATCH_EMULATE_CALLS | BATCH_EXACT_GRID)
         return y
     csoxr_divide_proc.__name__ = "csoxr_divide_proc_" + _DT_NAME[code]
     return csoxr_divide_proc
@@ -320,7 +324,7 @@ def _make_split_ch(code):
         out_pos, _ = resample_batch_raw(x.ctypes.data, ybuf.ctypes.data, in_rate=in_rate, out_rate=out_rate,
                                         quality=int(quality), dtype_code=code, n_clips=1, channels=ch, ilen=ilen,
                                         in_strides=(0, 1, st), out_strides=(0, 1, olen), olen=olen,
-                                        flags=BATCH_EMULATE_CALLS | BATCH_SPLIT_SEMANTICS)
+                                        flags=BATCH_EMULATE_CALLS | BATCH_SPLIT_SEMANTICS | BATCH_EXACT_GRID)
         # strided view over the over-allocated buffer, like the reference (soxr_ext.cpp:358)
         return np.lib.stride_tricks.as_strided(ybuf, shape=(out_pos, ch),
                                                strides=(x.itemsize, olen * x.itemsize))

@@ -5,8 +5,9 @@ unmodified reference and (2) the oracle restatement on the same seeded inputs.
 Tolerances (BASELINE.json north_star): float32 I/O within 1e-6 RMS of libsoxr on
 unit-variance noise; float64 I/O (f64 engine) within 1e-11 RMS; integers: see
 SURVEY.md section 7-H2 -- K7 itself is bit-exact given the reference's float
-stream, end-to-end ints are compared after rounding (>= 99 % equal, |delta| <= 1
-without dither, |delta| <= 2 with the reference's data-salted dither).
+stream, end-to-end ints are compared after rounding (|delta| <= 1 and >= 99.7 % equal
+on these short vectors without dither -- the full-size figure, >= 99.9 %, is asserted in
+test_gpu_live_ref.py -- and |delta| <= 2 with the reference's data-salted dither).
 """
 import numpy as np
 import pytest
@@ -66,7 +67,7 @@ def test_int_matches_reference_after_rounding(name):
                                     olen=ref.shape[0], flags=soxr_ext.BATCH_NO_DITHER)
         nd2 = nd[:, None] if nd.ndim == 1 else nd
         dd = np.abs(y2.astype(np.int64) - nd2)
-        assert dd.max() <= 1 and (dd == 0).mean() >= 0.99
+        assert dd.max() <= 1 and (dd == 0).mean() >= 0.997
     else:
         # int32 at 2^31 scale: VHQ runs the f64 engine -> exact after rounding up to 1 LSB;
         full = float(np.abs(ref).max())
@@ -111,7 +112,13 @@ def test_device_k7_saturation_and_clip_count():
         assert clips == want_clips and s2 == sd
 
 
-@pytest.mark.parametrize('in_rate, out_rate', [(44100, 32000), (32000, 44100)])
+# (44100, 32000) and (32000, 44100) are the reference's own pairs; the others are the ratio families of the
+# single-pass frequency-domain kernel, where the same bit-for-bit contract holds (the whole-signal drivers and
+# streams all evaluate the reference's block grid; only soxr.resample_batch uses the faster kernel by default)
+RATE_PAIRS = [(44100, 32000), (32000, 44100), (48000, 44100), (44100, 48000), (96000, 48000), (48000, 16000)]
+
+
+@pytest.mark.parametrize('in_rate, out_rate', RATE_PAIRS)
 @pytest.mark.parametrize('dtype', [np.float32, np.float64])
 def test_divide_match(in_rate, out_rate, dtype):
     # reference tests/test_resample.py:46-57: three drivers agree bit-exactly
@@ -124,11 +131,12 @@ def test_divide_match(in_rate, out_rate, dtype):
     assert y_split.strides[0] == y_split.itemsize
 
 
-@pytest.mark.parametrize('length', [0, 1, 2, 99, 100, 101, 31999, 32000, 32001, 44100, 66150])
+@pytest.mark.parametrize('length', [0, 1, 2, 99, 100, 101, 31999, 32000, 32001, 34828, 34829, 34830, 44099, 44100, 44101,
+                                    47999, 48000, 48001, 66149, 66150, 266151])
 def test_length_match(length):
-    # reference tests/test_resample.py:60-71
-    x = np.random.default_rng(2).standard_normal((66150, 2)).astype(np.float32)
-    for in_rate, out_rate in [(44100, 32000), (32000, 44100)]:
+    # reference tests/test_resample.py:60-71 (all of its lengths)
+    x = np.random.default_rng(2).standard_normal((266151, 2)).astype(np.float32)
+    for in_rate, out_rate in [(44100, 32000), (32000, 44100), (48000, 44100)]:
         y_oneshot = soxr._resample_oneshot(x[:length], in_rate, out_rate)
         y_divide = soxr.resample(x[:length], in_rate, out_rate)
         y_split = soxr.resample(np.asfortranarray(x)[:length], in_rate, out_rate)
@@ -163,14 +171,12 @@ def _stream(x, in_rate, out_rate, chunk, dtype, quality='HQ'):
     return np.concatenate(ys), counts, delays
 
 
-@pytest.mark.parametrize('in_rate, out_rate', [(44100, 32000), (32000, 44100)])
+@pytest.mark.parametrize('in_rate, out_rate', [(44100, 32000), (32000, 44100), (48000, 44100), (96000, 48000)])
 @pytest.mark.parametrize('chunk_size', [17, 509, 44100])
-@pytest.mark.parametrize('length', [0, 100, 31999, 44100])
+@pytest.mark.parametrize('length', [0, 100, 31999, 44100, 166151])
 @pytest.mark.parametrize('dtype', ['float32', np.float64])
 def test_stream_length(in_rate, out_rate, chunk_size, length, dtype):
-    # reference tests/test_resample.py:105-116: stream == one-shot, bit-exact
-    if chunk_size == 17 and length > 32000:
-        pytest.skip("many tiny GPU calls; covered by the 31999 case")
+    # reference tests/test_resample.py:105-116 (all of its lengths and chunk sizes): stream == one-shot, bit-exact
     x = np.random.default_rng(4).standard_normal((length, 1)).astype(dtype)
     y_oneshot = soxr._resample_oneshot(x, in_rate, out_rate)
     y_stream, _, _ = _stream(x, in_rate, out_rate, chunk_size, dtype)
@@ -194,11 +200,9 @@ def test_stream_counts_delays_match_reference(name):
         assert np.allclose(y, soxr.resample(x, s['in_rate'], s['out_rate'], s['quality']), atol=2)
     else:
         assert rms(y - orc) <= TOL_F32
-        # bit-identical to the one-shot driver on the reference's block grid (tests/test_resample.py:109-116);
-        # soxr.resample may take the single-pass frequency-domain kernel (VHQ float32 at 160:147): same
-        # operator, float32 rounding apart
+        # bit-identical to the one-shot drivers (tests/test_resample.py:46-57,109-116), at every ratio
         assert np.all(y == soxr._resample_oneshot(x, s['in_rate'], s['out_rate'], s['quality']))
-        assert rms(y.astype(np.float64) - soxr.resample(x, s['in_rate'], s['out_rate'], s['quality'])) <= 5e-7
+        assert np.all(y == soxr.resample(x, s['in_rate'], s['out_rate'], s['quality']))
 
 
 @pytest.mark.parametrize('in_rate, out_rate', [(48000, 22050), (8000, 48000)])
@@ -211,6 +215,24 @@ def test_stream_int(in_rate, out_rate, chunk_size, length, dtype):
     y_oneshot = soxr._resample_oneshot(x, in_rate, out_rate)
     y_stream, _, _ = _stream(x, in_rate, out_rate, chunk_size, dtype)
     assert np.allclose(y_oneshot, y_stream, atol=2)
+
+
+def test_stream_clear_resets_clip_counter_int16():
+    # soxr_clear zeroes the clip counter (soxr.c:609-628); the device-side accumulator must follow
+    x = np.where(np.sin(2 * np.pi * np.arange(4000) / 100.0) >= 0, 32767, -32768).astype(np.int16)[:, None]
+    # full-scale 480 Hz square wave: the band-limited result overshoots (Gibbs) and saturates
+    rs = soxr.ResampleStream(48000, 44100, 1, dtype='int16')
+    rs.resample_chunk(x, last=True)
+    assert rs.num_clips() > 0
+    rs.clear()
+    assert rs.num_clips() == 0
+    rs.resample_chunk(np.zeros((4000, 1), np.int16), last=True)
+    assert rs.num_clips() == 0
+    n1 = soxr.ResampleStream(48000, 44100, 1, dtype='int16')
+    n1.resample_chunk(x, last=True)
+    rs.clear()
+    rs.resample_chunk(x, last=True)
+    assert rs.num_clips() == n1.num_clips()
 
 
 def test_stream_clear_delay_and_input_after_last():
@@ -280,15 +302,33 @@ def test_multithread(num_task):
 def test_batch_matches_per_clip_and_torch_device_path():
     import torch
     x = np.random.default_rng(9).standard_normal((5, 7000, 2)).astype(np.float32)
-    yb = soxr.resample_batch(x, 48000, 44100, 'VHQ')
+    yb = soxr.resample_batch(x, 48000, 44100, 'VHQ')                     # single-pass frequency-domain kernel
+    ye = soxr.resample_batch(x, 48000, 44100, 'VHQ', exact_grid=True)    # the reference's block grid
     for b in range(5):
-        assert np.all(yb[b] == soxr.resample(x[b], 48000, 44100, 'VHQ'))
+        r = soxr.resample(x[b], 48000, 44100, 'VHQ')
+        assert np.all(ye[b] == r)
+        assert rms(yb[b].astype(np.float64) - r) <= 5e-7
     yt = soxr.resample_batch(torch.from_numpy(x).cuda(), 48000, 44100, 'VHQ')
     torch.cuda.synchronize()
     assert np.all(yt.cpu().numpy() == yb)
     xm = x[:, :, 0].copy()
-    ym = soxr.resample_batch(xm, 48000, 44100, 'HQ')
+    ym = soxr.resample_batch(xm, 48000, 44100, 'HQ', exact_grid=True)
     assert np.all(ym[3] == soxr.resample(xm[3], 48000, 44100, 'HQ'))
+    # int16: the batch replays each clip's call partition, so exact-grid batches equal soxr.resample bit for bit
+    xi = np.round(x[:, :, 0] * 5000).astype(np.int16)
+    yi = soxr.resample_batch(xi, 96000, 48000, 'HQ', exact_grid=True)
+    for b in range(5):
+        assert np.all(yi[b] == soxr.resample(xi[b], 96000, 48000, 'HQ'))
+    # a caller-supplied `out` must be exactly what the call would allocate
+    good = np.empty_like(yb)
+    assert soxr.resample_batch(x, 48000, 44100, 'VHQ', out=good) is good and np.all(good == yb)
+    for bad in (np.empty((5, 6430, 2), np.float32), np.empty(yb.shape, np.float64), np.empty((5, 2, 6431), np.float32).transpose(0, 2, 1)):
+        with pytest.raises(ValueError):
+            soxr.resample_batch(x, 48000, 44100, 'VHQ', out=bad)
+    with pytest.raises(ValueError):
+        soxr.resample_batch(torch.from_numpy(x).cuda(), 48000, 44100, 'VHQ', out=torch.empty(yb.shape, dtype=torch.float32))
+    with pytest.raises(TypeError):
+        soxr.resample_batch(x, 48000, 44100, 'VHQ', stream="0")
 
 
 def test_linearity_and_shift_properties_full_size():
@@ -329,12 +369,19 @@ def test_fdr_layouts_and_one_shot_drivers():
     want = O.resample_f64(x, 48000, 44100, O.VHQ)
     y_div = soxr.resample(x, 48000, 44100, 'VHQ')                        # C order: divide_proc driver
     y_split = soxr.resample(np.asfortranarray(x), 48000, 44100, 'VHQ')   # Fortran order: split_ch driver
-    y_one = soxr._resample_oneshot(x, 48000, 44100, 'VHQ')               # reference block grid
-    assert np.all(y_div == y_split)
-    for y in (y_div, y_one):
+    y_one = soxr._resample_oneshot(x, 48000, 44100, 'VHQ')
+    assert np.all(y_div == y_split) and np.all(y_div == y_one)            # reference block grid in all three
+    y_fdr = soxr.resample_batch(x[None], 48000, 44100, 'VHQ')[0]          # single-pass kernel, interleaved stereo
+    y_fdr_split = np.empty((y_one.shape[0], 2), np.float32, order='F')    # ... and planar (split-channel) buffers
+    xf = np.asfortranarray(x)
+    soxr_ext.resample_batch_raw(xf.ctypes.data, y_fdr_split.ctypes.data, in_rate=48000, out_rate=44100, quality=soxr.VHQ,
+                                dtype_code=0, n_clips=1, channels=2, ilen=len(x), in_strides=(0, 1, len(x)),
+                                out_strides=(0, 1, y_one.shape[0]), olen=y_one.shape[0])
+    assert np.all(y_fdr == y_fdr_split)
+    for y in (y_div, y_fdr):
         assert rms(y.astype(np.float64) - want) <= TOL_F32
-    assert rms(y_div.astype(np.float64) - y_one) <= 5e-7
-    y_m = soxr.resample(x[:, 0].copy(), 48000, 44100, 'VHQ')             # mono 1-D
+    assert rms(y_fdr.astype(np.float64) - y_one) <= 5e-7
+    y_m = soxr.resample_batch(x[None, :, 0].copy(), 48000, 44100, 'VHQ')[0]   # mono: block-paired transforms
     assert rms(y_m.astype(np.float64) - want[:, 0]) <= TOL_F32
 
 
