@@ -93,11 +93,28 @@ B200SOXR_API char const *b200soxr_version(void);
  *       609-628,601-605).  `in`/`out` are HOST pointers unless the handle was
  *      created with B200SOXR_RT_DEVICE_IO in runtime_spec.flags. ---------------- */
 #define B200SOXR_RT_DEVICE_IO 0x100ul   /* extension: in/out of process() are device pointers */
+/* extension: low-latency streaming.  The reference returns output in bursts of one FFT block (about 1000 samples,
+ * libsoxr/README:57-61); with this flag every call returns ALL output whose filter support has arrived (latency =
+ * half the filter length, about 3 ms at 48 kHz HQ), computed by the direct-form kernels.  Results stay within the
+ * parity budget of the reference but are not bit-identical to the default mode; b200soxr_delay() follows
+ * cr.c:578-581 with this mode's own output count. */
+#define B200SOXR_RT_LOW_LATENCY 0x200ul
 
 B200SOXR_API b200soxr_t b200soxr_create(double input_rate, double output_rate, unsigned num_channels,
                                         b200soxr_error_t *error, b200soxr_io_spec_t const *io_spec,
                                         b200soxr_quality_spec_t const *quality_spec,
                                         b200soxr_runtime_spec_t const *runtime_spec);
+/* extension: ONE handle for `num_streams` independent streams of `num_channels` channels each that are fed in
+ * lockstep (same ilen every call) -- what a server running many ResampleStreams would otherwise do with
+ * num_streams soxr_t handles and num_streams soxr_process calls (src/soxr_ext.cpp:129-188 per stream).  Every
+ * b200soxr_process call on it takes `in` as [stream][ilen][channel] and writes `out` packed as
+ * [stream][*odone][channel] (olen is the per-stream capacity; all streams return the same *odone); results,
+ * per-call counts, delay and dither are per stream exactly those of num_streams separate handles. */
+B200SOXR_API b200soxr_t b200soxr_create_batch(double input_rate, double output_rate, unsigned num_streams,
+                                              unsigned num_channels, b200soxr_error_t *error,
+                                              b200soxr_io_spec_t const *io_spec,
+                                              b200soxr_quality_spec_t const *quality_spec,
+                                              b200soxr_runtime_spec_t const *runtime_spec);
 /* in == NULL  => end of input; flush (soxr.h:131-133).  For split (*_S) types
  * in/out are arrays of per-channel pointers (soxr.h:81-87). */
 B200SOXR_API b200soxr_error_t b200soxr_process(b200soxr_t p, void const *in, size_t ilen, size_t *idone,

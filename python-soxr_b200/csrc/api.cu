@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <memory>
 #include <mutex>
 #include <new>
@@ -79,6 +80,15 @@ bool arith_double_for(const QSpec &q, int itype, int otype) {
   return strict;
 }
 
+// B200SOXR_TRACE_TIMING=1: per-handle wall-clock breakdown of b200soxr_process, printed to stderr by b200soxr_delete
+// (where the time of a stream call goes: history append, queueing device work, waiting for it, copy-out)
+const bool kTraceTiming = [] { const char *e = std::getenv("B200SOXR_TRACE_TIMING"); return e && e[0] == '1'; }();
+inline double now_us() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return double(ts.tv_sec) * 1e6 + double(ts.tv_nsec) * 1e-3;
+}
+
 size_t div_len_of(double in_rate, double out_rate) {          // soxr_ext.cpp:71,239
   return size_t(std::max(1000., 48000 * in_rate / out_rate));
 }
@@ -91,62 +101,137 @@ size_t div_len_of(double in_rate, double out_rate) {          // soxr_ext.cpp:71
 struct b200soxr {
   int device = -1;        // the CUDA device this handle's plan, stream and buffers live on
   unsigned channels = 0;
+  unsigned n_streams = 1; // batched handle (b200soxr_create_batch): independent streams of `channels` channels in lockstep
   double io_ratio = 0;
   b200soxr_io_spec_t io{};
   QSpec q;
   RSpec r;
   bool device_io = false;
+  bool low_latency = false;   // B200SOXR_RT_LOW_LATENCY: direct-form kernels, every output whose support has arrived
   std::shared_ptr<DevicePlan> dp;
   std::unique_ptr<CallEmu> emu;
   Workspace *ws = nullptr;
   cudaStream_t stream = nullptr;
+  // Input history, one of two homes:
+  //  * host_hist: mapped pinned HOST memory in the caller's own dtype, [stream][frame][channel].  A call that returns
+  //    no output is then a memcpy and nothing else (no launch, no copy engine, no synchronise); a call that returns
+  //    output is ONE launch whose first kernel reads the history over PCIe (K1 fused) and whose last kernel writes
+  //    the result into mapped pinned memory (K7 fused), plus one synchronise.  This is the home for streams fed in
+  //    small chunks (real-time use, BASELINE configs[2]).
+  //  * xbuf: planar engine-precision DEVICE memory (large chunks, split layouts, device I/O).
+  // A handle starts on the host and moves to the device for good at the first chunk above the zero-copy size.
+  bool host_hist = false;
+  PinnedBuf hx;
+  size_t hx_cap = 0;      // frames per stream in hx
   DevBuf xbuf, clips_dev, seed_dev;
   size_t x_cap = 0;       // elements per signal in xbuf
   long x_base = 0, x_hi = 0, n_in_total = -1, out_done = 0;
   size_t clips = 0;
-  unsigned long long seed = 0;
+  unsigned long long seed = 0;   // create-time dither seed (soxr.c:439); the running per-stream seeds live in seed_dev
   bool flushing = false;
   const char *error = nullptr;
-  std::vector<const void *> in_ptrs;
-  std::vector<void *> out_ptrs;
-  // small host chunks (streaming): two mapped pinned staging buffers used alternately, each fenced by an event
-  // recorded behind the K1 launch that reads it, so a call that returns no output need not synchronise at all
-  PinnedBuf pin_in2[2];
-  cudaEvent_t in_ev[2] = {nullptr, nullptr};
-  bool in_ev_set[2] = {false, false};
-  int pin_toggle = 0;
+  double t_in = 0, t_queue = 0, t_wait = 0, t_out = 0;   // B200SOXR_TRACE_TIMING
+  unsigned long n_calls = 0, n_due = 0;
 
   ~b200soxr() {
+    if (kTraceTiming && n_calls)
+      std::fprintf(stderr, "b200soxr timing: %lu calls (%lu with output): append %.1f us, queue %.1f us, wait %.1f us, copy-out %.1f us per call\n",
+                   n_calls, n_due, t_in / n_calls, t_queue / n_calls, t_wait / n_calls, t_out / n_calls);
     DeviceGuard guard(device);
-    for (int i = 0; i < 2; ++i) {
-      if (in_ev[i]) { if (in_ev_set[i]) cudaEventSynchronize(in_ev[i]); cudaEventDestroy(in_ev[i]); }
-      pin_in2[i].release();
-    }
+    if (stream) cudaStreamSynchronize(stream);
+    hx.release();
     xbuf.release();
     clips_dev.release();
     seed_dev.release();
     if (ws) release_workspace(ws);
   }
+  unsigned n_sig() const { return n_streams * channels; }
   size_t esz() const { return dp->is_double ? 8 : 4; }
+  const char *reset_seeds(unsigned long long v) {
+    std::vector<unsigned long long> sd(n_streams, v);
+    B2_CUDA(cudaMemcpyAsync(seed_dev.p, sd.data(), sd.size() * 8, cudaMemcpyHostToDevice, stream));
+    B2_CUDA(cudaStreamSynchronize(stream));   // sd is a stack-owned staging vector
+    return nullptr;
+  }
   const char *init_state() {
     emu.reset(new CallEmu(dp->plan));
     x_base = x_hi = out_done = 0;
     n_in_total = -1;
     flushing = false;
+    host_hist = !device_io && !(io.itype & B200SOXR_SPLIT);
     return nullptr;
   }
+  // ---- host-side history ------------------------------------------------------------------------------------
+  // make room for `extra` more frames per stream, dropping history no output can need
+  const char *grow_host_history(size_t extra) {
+    const long keep_from = std::max(x_base, std::min(x_hi, history_needed_from(*dp, out_done, low_latency)));
+    const size_t live = size_t(x_hi - keep_from);
+    const size_t fsz = size_t(channels) * dtype_size(io.itype & 3);
+    if (size_t(x_hi - x_base) + extra <= hx_cap) return nullptr;
+    if (live + extra <= hx_cap) {        // compact in place
+      for (unsigned b = 0; b < n_streams; ++b) {
+        char *row = static_cast<char *>(hx.p) + size_t(b) * hx_cap * fsz;
+        std::memmove(row, row + size_t(keep_from - x_base) * fsz, live * fsz);
+      }
+      x_base = keep_from;
+      return nullptr;
+    }
+    size_t new_cap = std::max<size_t>(4096, (live + extra) * 2);
+    PinnedBuf nb;
+    if (const char *e = nb.reserve(new_cap * fsz * n_streams)) return e;
+    for (unsigned b = 0; b < n_streams; ++b)
+      std::memcpy(static_cast<char *>(nb.p) + size_t(b) * new_cap * fsz,
+                  static_cast<char *>(hx.p) + (size_t(b) * hx_cap + size_t(keep_from - x_base)) * fsz, live * fsz);
+    hx.release();
+    hx = nb;
+    hx_cap = new_cap;
+    x_base = keep_from;
+    return nullptr;
+  }
+  SigDesc host_desc() const {
+    SigDesc d;
+    d.p = hx.p; d.dtype = io.itype & 3; d.channels = channels;
+    d.clip_stride = (long long)(hx_cap * channels); d.frame_stride = channels; d.chan_stride = 1;
+    d.base = x_base; d.vlo = std::max(0L, x_base); d.vhi = x_hi;
+    return d;
+  }
+  // move the live history into planar device memory (first large chunk): K1 reads the pinned rows
+  const char *migrate_to_device(size_t extra) {
+    const long keep_from = std::max(x_base, std::min(x_hi, history_needed_from(*dp, out_done, low_latency)));
+    const size_t live = size_t(x_hi - keep_from);
+    size_t new_cap = std::max<size_t>(4096, (live + extra) * 2);
+    new_cap = (new_cap + 63) & ~size_t(63);
+    xbuf.release();
+    if (const char *e = xbuf.reserve(new_cap * n_sig() * esz())) return e;
+    x_cap = new_cap;
+    if (live) {
+      IoLayout lay;
+      lay.dtype = io.itype & 3; lay.n_clips = n_streams; lay.channels = channels;
+      lay.clip_stride = (long long)(hx_cap * channels); lay.frame_stride = channels; lay.chan_stride = 1;
+      const char *src = static_cast<const char *>(hx.p) + size_t(keep_from - x_base) * channels * dtype_size(io.itype & 3);
+      if (const char *e = convert_in(lay, src, live, dp->is_double, xbuf.p, x_cap, 0, stream)) return e;
+      B2_CUDA(cudaStreamSynchronize(stream));
+    }
+    x_base = keep_from;
+    host_hist = false;
+    hx.release();
+    hx_cap = 0;
+    return nullptr;
+  }
+  // ---- device-side history ----------------------------------------------------------------------------------
   // make room for `extra` more samples per signal, dropping history no output can need
   const char *grow_history(size_t extra) {
-    const long keep_from = std::max(x_base, std::min(x_hi, history_needed_from(*dp, out_done)));
+    const long keep_from = std::max(x_base, std::min(x_hi, history_needed_from(*dp, out_done, low_latency)));
     const size_t live = size_t(x_hi - keep_from);
     const size_t es = esz();
+    const unsigned ns = n_sig();
     if (live + extra <= x_cap) {
       if (keep_from > x_base && live + extra + size_t(keep_from - x_base) > x_cap) {
         // compact in place (per signal; ranges may overlap -> go through scratch)
-        if (const char *e = ws->misc.reserve(std::max<size_t>(1, live * channels) * es)) return e;
+        if (const char *e = ws->misc.reserve(std::max<size_t>(1, live * ns) * es)) return e;
         B2_CUDA(cudaMemcpy2DAsync(ws->misc.p, live * es, static_cast<char *>(xbuf.p) + size_t(keep_from - x_base) * es,
-                                  x_cap * es, live * es, channels, cudaMemcpyDeviceToDevice, stream));
-        B2_CUDA(cudaMemcpy2DAsync(xbuf.p, x_cap * es, ws->misc.p, live * es, live * es, channels,
+                                  x_cap * es, live * es, ns, cudaMemcpyDeviceToDevice, stream));
+        B2_CUDA(cudaMemcpy2DAsync(xbuf.p, x_cap * es, ws->misc.p, live * es, live * es, ns,
                                   cudaMemcpyDeviceToDevice, stream));
         x_base = keep_from;
       }
@@ -156,16 +241,33 @@ struct b200soxr {
     size_t new_cap = std::max<size_t>(4096, (live + extra) * 2);
     new_cap = (new_cap + 63) & ~size_t(63);
     DevBuf nb;
-    if (const char *e = nb.reserve(new_cap * channels * es)) return e;
+    if (const char *e = nb.reserve(new_cap * ns * es)) return e;
     if (live)
       B2_CUDA(cudaMemcpy2DAsync(nb.p, new_cap * es, static_cast<char *>(xbuf.p) + size_t(keep_from - x_base) * es,
-                                x_cap * es, live * es, channels, cudaMemcpyDeviceToDevice, stream));
+                                x_cap * es, live * es, ns, cudaMemcpyDeviceToDevice, stream));
     B2_CUDA(cudaStreamSynchronize(stream));
     xbuf.release();
     xbuf = nb;
     x_cap = new_cap;
     x_base = keep_from;
     return nullptr;
+  }
+  // low-latency mode: number of outputs [0, n) whose whole filter support has arrived (all of them once flushing)
+  long outputs_ready() const {
+    const long total = long(output_frames(io_ratio, size_t(n_in_total >= 0 ? n_in_total : x_hi)));
+    if (n_in_total >= 0) return total;
+    long lo = out_done, hi = total + 1;          // outputs [0, lo) are ready; [0, hi) are not (zero-phase look-ahead)
+    if (outputs_need(hi) <= x_hi) return hi;     // (degenerate: filters shorter than one sample)
+    while (hi - lo > 1) {
+      const long mid = lo + (hi - lo) / 2;
+      if (outputs_need(mid) <= x_hi) lo = mid; else hi = mid;
+    }
+    return lo;
+  }
+  long outputs_need(long n_out) const {          // input frames [0, need) read by outputs [0, n_out)
+    long need = n_out;
+    for (size_t s = dp->plan.stages.size(); s-- > 0;) need = stage_input_needed(dp->plan.stages[s], need);
+    return need;
   }
 };
 
@@ -246,9 +348,9 @@ b200soxr_error_t b200soxr_emulate_calls(double in_rate, double out_rate, unsigne
   return nullptr;
 }
 
-b200soxr_t b200soxr_create(double input_rate, double output_rate, unsigned num_channels,
-                           b200soxr_error_t *error0, b200soxr_io_spec_t const *io_spec,
-                           b200soxr_quality_spec_t const *q_spec, b200soxr_runtime_spec_t const *rt_spec) {
+static b200soxr_t create_handle(double input_rate, double output_rate, unsigned n_streams, unsigned num_channels,
+                                b200soxr_error_t *error0, b200soxr_io_spec_t const *io_spec,
+                                b200soxr_quality_spec_t const *q_spec, b200soxr_runtime_spec_t const *rt_spec) {
   const char *error = nullptr;
   b200soxr *p = nullptr;
   const double io_ratio = output_rate != 0 ? (input_rate != 0 ? input_rate / output_rate : -1)
@@ -256,21 +358,25 @@ b200soxr_t b200soxr_create(double input_rate, double output_rate, unsigned num_c
   if (q_spec && q_spec->e) error = static_cast<const char *>(q_spec->e);
   else if (io_spec && (io_spec->e || (io_spec->itype | io_spec->otype) >= B200SOXR_SPLIT * 2))
     error = "invalid io datatype(s)";
-  else if (!num_channels) error = "invalid # of channels";
+  else if (!num_channels || !n_streams) error = "invalid # of channels";
   else if (!(io_ratio > 0)) error = "I/O ratio out-of-range";
   else if (!device_ok()) error = kNoDevice;
   if (!error && !(p = new (std::nothrow) b200soxr())) error = "malloc failed";
   if (p) {
     if (cudaGetDevice(&p->device) != cudaSuccess) { cudaGetLastError(); p->device = 0; }
     p->channels = num_channels;
+    p->n_streams = n_streams;
     p->io_ratio = io_ratio;
     if (io_spec) p->io = *io_spec;
     else { std::memset(&p->io, 0, sizeof p->io); p->io.scale = 1; }
     p->q = q_spec ? to_qspec(*q_spec) : quality_spec(B200SOXR_HQ, 0);
     p->r = to_rspec(rt_spec);
     p->device_io = rt_spec && (rt_spec->flags & B200SOXR_RT_DEVICE_IO);
+    p->low_latency = rt_spec && (rt_spec->flags & B200SOXR_RT_LOW_LATENCY);
     if (((p->io.itype ^ p->io.otype) & B200SOXR_SPLIT))
       error = "b200soxr: input and output must both be interleaved or both split";
+    else if (n_streams > 1 && (p->io.itype & B200SOXR_SPLIT))
+      error = "b200soxr: batched stream handles take interleaved layouts only";
     const double scale = p->io.scale * kFullScale[p->io.otype & 3] / kFullScale[p->io.itype & 3];   // soxr.c:435-436
     // deterministic dither seed, soxr.c:439
     unsigned long long bits;
@@ -281,8 +387,9 @@ b200soxr_t b200soxr_create(double input_rate, double output_rate, unsigned num_c
       p->ws = acquire_workspace();
       p->stream = (rt_spec && rt_spec->e) ? static_cast<cudaStream_t>(rt_spec->e) : p->ws->stream;
       error = p->clips_dev.reserve(8);
-      if (!error) error = p->seed_dev.reserve(8);
+      if (!error) error = p->seed_dev.reserve(8 * size_t(n_streams));
       if (!error && cudaMemset(p->clips_dev.p, 0, 8) != cudaSuccess) error = "cudaMemset failed";
+      if (!error) error = p->reset_seeds(p->seed);
       if (!error) error = p->init_state();
     }
     if (error) { delete p; p = nullptr; }
@@ -291,7 +398,26 @@ b200soxr_t b200soxr_create(double input_rate, double output_rate, unsigned num_c
   return p;
 }
 
-double b200soxr_delay(b200soxr_t p) { return (p && !p->error && p->emu) ? p->emu->delay() : 0; }
+b200soxr_t b200soxr_create(double input_rate, double output_rate, unsigned num_channels,
+                           b200soxr_error_t *error0, b200soxr_io_spec_t const *io_spec,
+                           b200soxr_quality_spec_t const *q_spec, b200soxr_runtime_spec_t const *rt_spec) {
+  return create_handle(input_rate, output_rate, 1, num_channels, error0, io_spec, q_spec, rt_spec);
+}
+
+b200soxr_t b200soxr_create_batch(double input_rate, double output_rate, unsigned num_streams, unsigned num_channels,
+                                 b200soxr_error_t *error0, b200soxr_io_spec_t const *io_spec,
+                                 b200soxr_quality_spec_t const *q_spec, b200soxr_runtime_spec_t const *rt_spec) {
+  return create_handle(input_rate, output_rate, num_streams, num_channels, error0, io_spec, q_spec, rt_spec);
+}
+
+double b200soxr_delay(b200soxr_t p) {
+  if (!p || p->error || !p->emu) return 0;
+  if (!p->low_latency) return p->emu->delay();
+  // cr.c:578-581 with this mode's own output count: samples_in / io_ratio - samples_out before the flush,
+  // what is left of round(samples_in / io_ratio) after it (cr.c:541-547)
+  if (p->n_in_total >= 0) return double(long(output_frames(p->io_ratio, size_t(p->n_in_total))) - p->out_done);
+  return double(p->x_hi) / p->io_ratio - double(p->out_done);
+}
 size_t *b200soxr_num_clips(b200soxr_t p) { return &p->clips; }
 char const *b200soxr_engine(b200soxr_t p) { return p->dp->is_double ? "b200-cr64" : "b200-cr32"; }
 
@@ -305,7 +431,7 @@ b200soxr_error_t b200soxr_clear(b200soxr_t p) {
   p->error = nullptr;
   // the device-side accumulators k_rint_clip / k_dither_seeds add to restart as well
   if (p->clips_dev.p) B2_CUDA(cudaMemsetAsync(p->clips_dev.p, 0, 8, p->stream));
-  if (p->seed_dev.p) B2_CUDA(cudaMemsetAsync(p->seed_dev.p, 0, 8, p->stream));
+  if (const char *e = p->reset_seeds(0)) return e;
   return p->init_state();
 }
 
@@ -315,6 +441,13 @@ void b200soxr_delete(b200soxr_t p) { delete p; }   // ~b200soxr switches to the 
 static const size_t kZeroCopyBytes = [] {
   const char *v = std::getenv("B200SOXR_ZERO_COPY_KB");
   return size_t(v ? std::max(0L, std::atol(v)) : 256) << 10;
+}();
+
+// history windows up to this size are read by the kernels straight from mapped pinned memory; larger ones are
+// moved next to them by one DMA first
+static const size_t kDirectReadBytes = [] {
+  const char *v = std::getenv("B200SOXR_DIRECT_READ_KB");
+  return size_t(v ? std::max(0L, std::atol(v)) : 192) << 10;
 }();
 
 b200soxr_error_t b200soxr_process(b200soxr_t p, void const *in, size_t ilen0, size_t *idone0, void *out,
@@ -332,116 +465,144 @@ b200soxr_error_t b200soxr_process(b200soxr_t p, void const *in, size_t ilen0, si
   p->flushing |= (ilen == ilen0 && flush_requested);
   if (!out && olen) return p->error = "null output buffer pointer";
 
-  const unsigned ch = p->channels;
+  const unsigned ch = p->channels, B = p->n_streams, ns = p->n_sig();
   const bool split = (p->io.itype & B200SOXR_SPLIT) != 0;
   const int it = p->io.itype & 3, ot = p->io.otype & 3;
   cudaStream_t st = p->stream;
   Workspace *ws = p->ws;
   const char *e = nullptr;
+  bool queued = false;   // device work of this call is on the stream (the caller's buffers may still be in use)
+  const double t0 = kTraceTiming ? now_us() : 0;
 
-  int zc = -1;   // index of the mapped pinned staging buffer this call's input went through, if any
-  // ---- input: H2D + deinterleave/convert into the device history (soxr.c:640-660)
+  // ---- input (soxr.c:640-660): append to the history
   if (ilen && !p->emu->flushing()) {
-    if ((e = p->grow_history(ilen))) return p->error = e;
     const size_t isz = dtype_size(it);
-    const void *dev_in = in;
-    IoLayout lay;
-    lay.dtype = it;
-    lay.n_clips = 1;
-    lay.channels = ch;
-    if (p->device_io) {
-      if (split) return p->error = "b200soxr: device I/O supports interleaved layouts only";
-      lay.frame_stride = ch; lay.chan_stride = 1;
+    if (p->host_hist && ilen * ch * isz * B > kZeroCopyBytes)
+      if ((e = p->migrate_to_device(ilen))) return p->error = e;
+    if (p->host_hist) {
+      // small chunk (streaming): a memcpy into the mapped pinned history, nothing else
+      if ((e = p->grow_host_history(ilen))) return p->error = e;
+      const size_t fsz = size_t(ch) * isz;
+      for (unsigned b = 0; b < B; ++b)
+        std::memcpy(static_cast<char *>(p->hx.p) + (size_t(b) * p->hx_cap + size_t(p->x_hi - p->x_base)) * fsz,
+                    static_cast<const char *>(in) + size_t(b) * ilen * fsz, ilen * fsz);
     } else {
-      if (!split && ilen * ch * isz <= kZeroCopyBytes) {
-        // small chunk (streaming): no DMA at all.  The chunk is copied into pinned host memory that the device
-        // maps at the same address (UVA) and K1 reads it over PCIe: one launch instead of a staged pageable
-        // cudaMemcpy plus a launch.
-        zc = p->pin_toggle ^= 1;
-        if (p->in_ev_set[zc]) B2_CUDA(cudaEventSynchronize(p->in_ev[zc]));   // the K1 launch that last read this buffer
-        if ((e = p->pin_in2[zc].reserve(ilen * ch * isz))) return p->error = e;
-        std::memcpy(p->pin_in2[zc].p, in, ilen * ch * isz);
+      if ((e = p->grow_history(ilen))) return p->error = e;
+      const void *dev_in = in;
+      IoLayout lay;
+      lay.dtype = it;
+      lay.n_clips = B;
+      lay.channels = ch;
+      lay.clip_stride = (long long)(ilen * ch);
+      if (p->device_io) {
+        if (split) return p->error = "b200soxr: device I/O supports interleaved layouts only";
         lay.frame_stride = ch; lay.chan_stride = 1;
-        dev_in = p->pin_in2[zc].p;
       } else {
-      if ((e = ws->in_stage.reserve(ilen * ch * isz))) return p->error = e;
-      if (split) {
-        const void *const *ptrs = static_cast<const void *const *>(in);
-        for (unsigned c = 0; c < ch; ++c)
-          B2_CUDA(cudaMemcpyAsync(static_cast<char *>(ws->in_stage.p) + size_t(c) * ilen * isz, ptrs[c], ilen * isz,
-                                  cudaMemcpyHostToDevice, st));
-        lay.frame_stride = 1; lay.chan_stride = (long long)ilen;
-      } else {
-        B2_CUDA(cudaMemcpyAsync(ws->in_stage.p, in, ilen * ch * isz, cudaMemcpyHostToDevice, st));
-        lay.frame_stride = ch; lay.chan_stride = 1;
+        if ((e = ws->in_stage.reserve(ilen * ch * isz * B))) return p->error = e;
+        if (split) {
+          const void *const *ptrs = static_cast<const void *const *>(in);
+          for (unsigned c = 0; c < ch; ++c)
+            B2_CUDA(cudaMemcpyAsync(static_cast<char *>(ws->in_stage.p) + size_t(c) * ilen * isz, ptrs[c], ilen * isz,
+                                    cudaMemcpyHostToDevice, st));
+          lay.frame_stride = 1; lay.chan_stride = (long long)ilen;
+        } else {
+          B2_CUDA(cudaMemcpyAsync(ws->in_stage.p, in, ilen * ch * isz * B, cudaMemcpyHostToDevice, st));
+          lay.frame_stride = ch; lay.chan_stride = 1;
+        }
+        dev_in = ws->in_stage.p;
       }
-      dev_in = ws->in_stage.p;
-      }
-    }
-    if ((e = convert_in(lay, dev_in, ilen, p->dp->is_double, p->xbuf.p, p->x_cap, size_t(p->x_hi - p->x_base), st)))
-      return p->error = e;
-    if (zc >= 0) {
-      if (!p->in_ev[zc]) B2_CUDA(cudaEventCreateWithFlags(&p->in_ev[zc], cudaEventDisableTiming));
-      B2_CUDA(cudaEventRecord(p->in_ev[zc], st));
-      p->in_ev_set[zc] = true;
+      if ((e = convert_in(lay, dev_in, ilen, p->dp->is_double, p->xbuf.p, p->x_cap, size_t(p->x_hi - p->x_base), st)))
+        return p->error = e;
+      queued = true;
     }
     p->x_hi += long(ilen);
     p->emu->add_input(ilen);
   }
   if (p->flushing && p->n_in_total < 0) p->n_in_total = p->x_hi;
+  const double t1 = kTraceTiming ? now_us() : 0;
 
   // ---- output (soxr.c:664-733): how much the reference would return now
-  const size_t odone = p->emu->pull(olen, p->flushing);
+  size_t odone;
+  if (p->low_latency) {
+    if (p->flushing) p->emu->pull(0, true);   // keep the emulator's flushing state in step (input is refused after it)
+    odone = size_t(std::max(0L, std::min(long(olen), p->outputs_ready() - p->out_done)));
+  } else {
+    odone = p->emu->pull(olen, p->flushing);
+  }
   bool out_zero_copy = false;
   const bool int_out = ot >= B200SOXR_INT32;
-  if (odone || (ot == B200SOXR_INT16 && !(p->io.flags & B200SOXR_NO_DITHER))) {
+  const bool dith = ot == B200SOXR_INT16 && !(p->io.flags & B200SOXR_NO_DITHER);
+  if (odone || dith) {
     const size_t es = p->esz(), osz = dtype_size(ot);
     IoLayout lay;
     lay.dtype = ot;
-    lay.n_clips = 1;
+    lay.n_clips = B;
     lay.channels = ch;
+    lay.clip_stride = (long long)(odone * ch);     // batched handles: [stream][odone][channel], packed
     void *dev_out = out;
     if (p->device_io) { lay.frame_stride = ch; lay.chan_stride = 1; }
-    else if (!split && odone * ch * osz <= kZeroCopyBytes) {
+    else if (!split && odone * ch * osz * B <= kZeroCopyBytes) {
       // small result: the last kernel writes straight into mapped pinned host memory (K7 fused, no D2H copy)
-      if ((e = ws->pin_out.reserve(std::max<size_t>(1, odone * ch) * osz))) return p->error = e;
+      if ((e = ws->pin_out.reserve(std::max<size_t>(1, odone * ch * B) * osz))) return p->error = e;
       dev_out = ws->pin_out.p;
       out_zero_copy = true;
       lay.frame_stride = ch; lay.chan_stride = 1;
     } else {
-      if ((e = ws->out_stage.reserve(std::max<size_t>(1, odone * ch) * osz))) return p->error = e;
+      if ((e = ws->out_stage.reserve(std::max<size_t>(1, odone * ch * B) * osz))) return p->error = e;
       dev_out = ws->out_stage.p;
       if (split) { lay.frame_stride = 1; lay.chan_stride = (long long)odone; }
       else { lay.frame_stride = ch; lay.chan_stride = 1; }
     }
-    const SigDesc xin = planar_desc(p->xbuf.p, p->dp->is_double, p->x_cap, p->x_base, std::max(0L, p->x_base), p->x_hi);
+    SigDesc xin;
+    if (p->host_hist) {
+      // One DMA moves the window of the pinned history these outputs read ([stream][frames][channel] rows) next to
+      // the kernels; they take it from there in the caller's dtype and layout (K1 fused).  (Reading the mapped
+      // host rows from the kernel instead costs a PCIe round trip per load: 30 us for one 2048-point block.)
+      const long lo = std::max(p->x_base, std::min(p->x_hi, history_needed_from(*p->dp, p->out_done, p->low_latency)));
+      const size_t frames = size_t(p->x_hi - lo), fsz = size_t(ch) * dtype_size(it);
+      if (frames * fsz * B <= kDirectReadBytes) {
+        xin = p->host_desc();    // a few blocks: the kernel reads the mapped pinned rows itself (no copy engine in the path)
+      } else {
+        if ((e = ws->in_stage.reserve(std::max<size_t>(1, frames * fsz * B)))) return p->error = e;
+        B2_CUDA(cudaMemcpy2DAsync(ws->in_stage.p, frames * fsz, static_cast<const char *>(p->hx.p) + size_t(lo - p->x_base) * fsz,
+                                  p->hx_cap * fsz, frames * fsz, B, cudaMemcpyHostToDevice, st));
+        xin.p = ws->in_stage.p; xin.dtype = it; xin.channels = ch;
+        xin.clip_stride = (long long)(frames * ch); xin.frame_stride = ch; xin.chan_stride = 1;
+        xin.base = lo; xin.vlo = std::max(0L, lo); xin.vhi = p->x_hi;
+      }
+    } else {
+      xin = planar_desc(p->xbuf.p, p->dp->is_double, p->x_cap, p->x_base, std::max(0L, p->x_base), p->x_hi);
+    }
+    const unsigned run_flags = p->low_latency ? unsigned(kRunGeneric) : 0u;
     if (!int_out) {
       // float output: the last launch writes the caller's layout directly (K7 fused)
       if (odone) {
         SigDesc od;
-        od.p = dev_out; od.dtype = ot; od.channels = ch; od.clip_stride = 0;
+        od.p = dev_out; od.dtype = ot; od.channels = ch; od.clip_stride = lay.clip_stride;
         od.frame_stride = lay.frame_stride; od.chan_stride = lay.chan_stride; od.base = p->out_done;
-        if ((e = run_range(*p->dp, xin, p->n_in_total, ch, ch, p->out_done, p->out_done + long(odone), od, ws, st)))
+        if ((e = run_range(*p->dp, xin, p->n_in_total, ns, ch, p->out_done, p->out_done + long(odone), od, ws, st, run_flags)))
           return p->error = e;
       }
     } else {
       const size_t ys = (std::max<size_t>(odone, 1) + 63) & ~size_t(63);
-      if ((e = ws->y.reserve(ys * ch * es))) return p->error = e;
+      if ((e = ws->y.reserve(ys * ns * es))) return p->error = e;
       if (odone) {
         const SigDesc yd = planar_desc(ws->y.p, p->dp->is_double, ys, p->out_done, 0, 0);
-        if ((e = run_range(*p->dp, xin, p->n_in_total, ch, ch, p->out_done, p->out_done + long(odone), yd, ws, st)))
+        if ((e = run_range(*p->dp, xin, p->n_in_total, ns, ch, p->out_done, p->out_done + long(odone), yd, ws, st, run_flags)))
           return p->error = e;
       }
       DitherCfg dc;
-      dc.enabled = ot == B200SOXR_INT16 && !(p->io.flags & B200SOXR_NO_DITHER);
+      dc.enabled = dith;
       dc.split = split;
-      dc.seed0 = p->seed;
+      dc.seed0 = 0;
+      dc.seed_in_dev = p->seed_dev.as<unsigned long long>();    // running per-stream seeds stay on the device
       dc.call_lens.push_back((long long)odone);
       dc.seed_end_dev = p->seed_dev.as<unsigned long long>();
       if ((e = convert_out(lay, dev_out, 0, odone, p->dp->is_double, ws->y.p, ys, dc, p->clips_dev.as<unsigned long long>(),
                            ws, st)))
         return p->error = e;
     }
+    queued = true;
     if (!p->device_io && odone && !out_zero_copy) {
       if (split) {
         void *const *ptrs = static_cast<void *const *>(out);
@@ -449,21 +610,26 @@ b200soxr_error_t b200soxr_process(b200soxr_t p, void const *in, size_t ilen0, si
           B2_CUDA(cudaMemcpyAsync(ptrs[c], static_cast<char *>(dev_out) + size_t(c) * odone * osz, odone * osz,
                                   cudaMemcpyDeviceToHost, st));
       } else
-        B2_CUDA(cudaMemcpyAsync(out, dev_out, odone * ch * osz, cudaMemcpyDeviceToHost, st));
+        B2_CUDA(cudaMemcpyAsync(out, dev_out, odone * ch * osz * B, cudaMemcpyDeviceToHost, st));
     }
     if (int_out) {
-      unsigned long long host[2] = {0, 0};
-      B2_CUDA(cudaMemcpyAsync(&host[0], p->clips_dev.p, 8, cudaMemcpyDeviceToHost, st));
-      const bool dith = ot == B200SOXR_INT16 && !(p->io.flags & B200SOXR_NO_DITHER);
-      if (dith) B2_CUDA(cudaMemcpyAsync(&host[1], p->seed_dev.p, 8, cudaMemcpyDeviceToHost, st));
+      unsigned long long host = 0;
+      B2_CUDA(cudaMemcpyAsync(&host, p->clips_dev.p, 8, cudaMemcpyDeviceToHost, st));
       B2_CUDA(cudaStreamSynchronize(st));
-      p->clips = size_t(host[0]);
-      if (dith) p->seed = host[1];
+      p->clips = size_t(host);
+      queued = false;
     }
   }
-  // nothing to hand back and the input already consumed from the caller's buffer: leave the K1 launch queued
-  if (!p->device_io && !(zc >= 0 && odone == 0)) B2_CUDA(cudaStreamSynchronize(st));
-  if (out_zero_copy && odone) std::memcpy(out, ws->pin_out.p, odone * ch * dtype_size(ot));
+  // host buffers are the caller's again on return; device I/O stays asynchronous on the handle's stream
+  const double t2 = kTraceTiming ? now_us() : 0;
+  if (queued && !p->device_io) B2_CUDA(cudaStreamSynchronize(st));
+  const double t3 = kTraceTiming ? now_us() : 0;
+  if (out_zero_copy && odone) std::memcpy(out, ws->pin_out.p, odone * ch * B * dtype_size(ot));
+  if (kTraceTiming) {
+    p->t_in += t1 - t0; p->t_queue += t2 - t1; p->t_wait += t3 - t2; p->t_out += now_us() - t3;
+    ++p->n_calls;
+    p->n_due += odone != 0;
+  }
   p->out_done += long(odone);
   if (idone0) *idone0 = ilen;
   if (odone0) *odone0 = odone;

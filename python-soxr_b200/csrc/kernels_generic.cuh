@@ -201,11 +201,11 @@ struct DitherBlock { long long start; long long n; };
 template <typename T>
 __global__ void k_dither_seeds(const T *__restrict__ Y, size_t y_stride, unsigned channels, unsigned n_clips,
                                const DitherBlock *__restrict__ blocks, unsigned n_blocks,
-                               unsigned long long seed0, bool split, ulonglong2 *__restrict__ seeds,
-                               unsigned long long *__restrict__ seed_end) {
+                               unsigned long long seed0, const unsigned long long *seed_in, bool split,
+                               ulonglong2 *__restrict__ seeds, unsigned long long *seed_end) {
   const unsigned clip = blockIdx.x * blockDim.x + threadIdx.x;
   if (clip >= n_clips) return;
-  unsigned long long seed = seed0;
+  unsigned long long seed = seed_in ? seed_in[clip] : seed0;   // (seed_in may alias seed_end: read before written)
   for (unsigned b = 0; b < n_blocks; ++b) {
     const long long st = blocks[b].start, n = blocks[b].n;
     if (!split)  // LSX_RINT_CLIP_2 salts once per call with channel 0 (rint-clip.h:104)

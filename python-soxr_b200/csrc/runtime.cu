@@ -265,8 +265,8 @@ const char *convert_out_int(const IoLayout &lay, void *out, size_t frame_off, si
     if (const char *e = ws->seeds.reserve(size_t(lay.n_clips) * nb * lay.channels * sizeof(ulonglong2))) return e;
     seeds = ws->seeds.as<ulonglong2>();
     k_dither_seeds<T><<<(lay.n_clips + 63) / 64, 64, 0, st>>>(Y, ys, lay.channels, lay.n_clips,
-                                                            ws->blocks.as<DitherBlock>(), nb, dc.seed0, dc.split,
-                                                            seeds, dc.seed_end_dev);
+                                                            ws->blocks.as<DitherBlock>(), nb, dc.seed0, dc.seed_in_dev,
+                                                            dc.split, seeds, dc.seed_end_dev);
     B2_COUNT_LAUNCH();
     B2_CUDA(cudaGetLastError());
   }
@@ -333,10 +333,10 @@ struct Range { long lo, hi; };
 
 // Output range of stage s-1 needed to produce outputs [r.lo, r.hi) of stage `last`,
 // where stages [s, last] run as one launch.
-Range input_range(const DevicePlan &dp, size_t s, size_t last, Range r) {
+Range input_range(const DevicePlan &dp, size_t s, size_t last, Range r, bool generic = false) {
   if (r.hi <= r.lo) return {0, 0};
   Range need;
-  if (dp.fft && dp.fft->stage_index == int(s)) {
+  if (!generic && dp.fft && dp.fft->stage_index == int(s)) {
     const RangeLH t = fft_stage_input_range(*dp.fft, r.lo, r.hi);
     need = {t.lo, t.hi};
   } else {
@@ -446,8 +446,8 @@ const char *run_range_t(const DevicePlan &dp, const SigDesc &in0, long n_in_tota
   }
   launches.back().r = {o0, o1};
   for (size_t i = launches.size() - 1; i > 0; --i)
-    launches[i - 1].r = input_range(dp, launches[i].first, launches[i].last, launches[i].r);
-  const Range xin = input_range(dp, launches[0].first, launches[0].last, launches[0].r);
+    launches[i - 1].r = input_range(dp, launches[i].first, launches[i].last, launches[i].r, (flags & kRunGeneric) != 0);
+  const Range xin = input_range(dp, launches[0].first, launches[0].last, launches[0].r, (flags & kRunGeneric) != 0);
   if (xin.hi > xin.lo && xin.lo < in0.base) return "internal: input history trimmed too far";
   if (n_in_total < 0 && xin.hi > in0.vhi) return "internal: output range needs input that has not arrived";
 
@@ -498,17 +498,17 @@ const char *run_range(const DevicePlan &dp, const SigDesc &in, long n_in_total, 
                       : run_range_t<float>(dp, in, n_in_total, n_sig, group, o0, o1, out, ws, stream, flags);
 }
 
-long history_needed_from(const DevicePlan &dp, long o) {
+long history_needed_from(const DevicePlan &dp, long o, bool generic) {
   Range r{o, o + 1};
   std::vector<std::pair<size_t, size_t>> launches;
   const size_t S = dp.plan.stages.size();
   for (size_t s = 0; s < S; ++s) {
-    const bool use_fft = dp.fft && dp.fft->stage_index == int(s);
+    const bool use_fft = !generic && dp.fft && dp.fft->stage_index == int(s);
     const size_t last = (use_fft && dp.fft->fused_poly) ? s + 1 : s;
     launches.push_back({s, last});
     s = last;
   }
-  for (size_t i = launches.size(); i-- > 0;) r = input_range(dp, launches[i].first, launches[i].second, r);
+  for (size_t i = launches.size(); i-- > 0;) r = input_range(dp, launches[i].first, launches[i].second, r, generic);
   return r.lo;
 }
 

@@ -147,7 +147,7 @@ const char *run_range(const DevicePlan &dp, const SigDesc &in, long n_in_total, 
                       long o0, long o1, const SigDesc &out, Workspace *ws, cudaStream_t stream, unsigned flags = 0);
 
 // Lowest input index any output >= o can still depend on (for history trimming).
-long history_needed_from(const DevicePlan &dp, long o);
+long history_needed_from(const DevicePlan &dp, long o, bool generic = false);   // generic: the direct-form kernels' ranges
 
 const char *convert_in(const IoLayout &lay, const void *dev_in, size_t n_frames, bool is_double, void *X,
                        size_t x_stride, size_t x_off, cudaStream_t stream);
@@ -156,6 +156,7 @@ struct DitherCfg {
   bool enabled = false;     // int16 and !NO_DITHER
   bool split = false;
   unsigned long long seed0 = 0;
+  const unsigned long long *seed_in_dev = nullptr;   // optional [n_clips]: per-clip start seeds on the device (streams)
   std::vector<long long> call_lens;   // frames per emulated call (sum == n_frames)
   unsigned long long *seed_end_dev = nullptr;   // optional [n_clips]
 };

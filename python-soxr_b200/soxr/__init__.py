@@ -64,13 +64,16 @@ class ResampleStream:
     (variable rate) is not provided by the B200 library and raises.
     """
 
-    def __init__(self, in_rate, out_rate, num_channels, dtype='float32', quality='HQ', vr=False):
+    def __init__(self, in_rate, out_rate, num_channels, dtype='float32', quality='HQ', vr=False, low_latency=False):
         _check_rates(in_rate, out_rate)
         _check_channels(num_channels)
         self._type = np.dtype(dtype)
         stype = _to_soxr_datatype(self._type)
         q = _quality_to_enum(quality)
-        self._csoxr = soxr_ext.CSoxr(in_rate, out_rate, num_channels, stype, q, vr)
+        # low_latency (B200 extension): return every output whose filter support has arrived (about half a filter
+        # length of delay) instead of the reference's FFT-block bursts; same filters, within the parity budget of
+        # the default mode but not bit-identical to it
+        self._csoxr = soxr_ext.CSoxr(in_rate, out_rate, num_channels, stype, q, vr, low_latency=low_latency)
         self._process = getattr(self._csoxr, 'process_{}'.format(self._type))
 
     def resample_chunk(self, x, last=False):
@@ -102,6 +105,53 @@ class ResampleStream:
 
     def set_io_ratio(self, in_rate, out_rate, slew_len=0):
         self._csoxr.set_io_ratio(in_rate / out_rate, slew_len)
+
+
+class ResampleStreamBatch:
+    """B200 extension: `n_streams` independent ResampleStreams of `num_channels` channels each, fed in lockstep
+    through ONE library handle (one launch per chunk for all of them instead of one per stream).
+
+    resample_chunk(x, last=False): x is [stream, frame, channel] (dtype as constructed); returns
+    [stream, frames_out, channel].  Per stream the samples, the per-call frame counts, delay() and the int16
+    dither are exactly those of a separate ResampleStream fed that stream's chunks.
+    """
+
+    def __init__(self, in_rate, out_rate, n_streams, num_channels, dtype='float32', quality='HQ', low_latency=False):
+        _check_rates(in_rate, out_rate)
+        _check_channels(num_channels)
+        if n_streams < 1 or n_streams * num_channels > _CH_LIMIT * 64:
+            raise ValueError('Stream num({}) out of limit'.format(n_streams))
+        self._type = np.dtype(dtype)
+        self._n = int(n_streams)
+        stype = _to_soxr_datatype(self._type)
+        q = _quality_to_enum(quality)
+        self._csoxr = soxr_ext.CSoxr(in_rate, out_rate, num_channels, stype, q, False, n_streams=max(2, self._n),
+                                     low_latency=low_latency) if self._n > 1 else \
+            soxr_ext.CSoxr(in_rate, out_rate, num_channels, stype, q, False, low_latency=low_latency)
+        self._process = getattr(self._csoxr, 'process_{}'.format(self._type))
+
+    def resample_chunk(self, x, last=False):
+        if type(x) != np.ndarray or x.dtype != self._type:
+            raise TypeError('Input should be a `np.ndarray` with matching dtype for ResampleStreamBatch({}).'
+                            .format(self._type))
+        if x.ndim != 3 or x.shape[0] != self._n:
+            raise ValueError('Input must be a [stream, frame, channel] array with {} streams'.format(self._n))
+        if self._n == 1:
+            return self._process(x[0], last)[np.newaxis]
+        return self._process(x, last)
+
+    def num_clips(self):
+        """Clipped samples so far, summed over the streams."""
+        return self._csoxr.num_clips()
+
+    def delay(self):
+        return self._csoxr.delay()
+
+    def clear(self):
+        self._csoxr.clear()
+
+    def engine(self):
+        return self._csoxr.engine()
 
 
 def resample(x, in_rate, out_rate, quality='HQ'):

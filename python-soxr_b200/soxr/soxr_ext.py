@@ -34,6 +34,7 @@ BATCH_EMULATE_CALLS, BATCH_ONESHOT_CALLS, BATCH_SPLIT_SEMANTICS = 8, 16, 32
 # frequency-domain kernel is what `soxr.resample_batch` / b200soxr_resample_batch use by default.
 BATCH_EXACT_GRID = 64
 RT_DEVICE_IO = 0x100
+RT_LOW_LATENCY = 0x200
 
 
 class _IoSpec(C.Structure):
@@ -77,6 +78,9 @@ def _load():
     L.b200soxr_create.restype = C.c_void_p
     L.b200soxr_create.argtypes = [C.c_double, C.c_double, C.c_uint, C.POINTER(C.c_char_p),
                                   C.POINTER(_IoSpec), C.POINTER(_QualitySpec), C.POINTER(_RuntimeSpec)]
+    L.b200soxr_create_batch.restype = C.c_void_p
+    L.b200soxr_create_batch.argtypes = [C.c_double, C.c_double, C.c_uint, C.c_uint, C.POINTER(C.c_char_p),
+                                        C.POINTER(_IoSpec), C.POINTER(_QualitySpec), C.POINTER(_RuntimeSpec)]
     L.b200soxr_process.restype = C.c_char_p
     L.b200soxr_process.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t),
                                    C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
@@ -196,53 +200,75 @@ def _div_len(in_rate, out_rate):
 
 
 class CSoxr:
-    """Stream handle; mirrors class CSoxr of the reference binding."""
+    """Stream handle; mirrors class CSoxr of the reference binding (soxr_ext.cpp:49-205).
 
-    def __init__(self, in_rate, out_rate, num_channels, ntype, quality, vr=False):
+    Extensions: `n_streams` > 1 makes ONE handle drive that many independent streams fed in lockstep
+    (b200soxr_create_batch; arrays are then [stream, frame, channel]); `low_latency` returns every output whose
+    filter support has arrived instead of the reference's FFT-block bursts (B200SOXR_RT_LOW_LATENCY)."""
+
+    def __init__(self, in_rate, out_rate, num_channels, ntype, quality, vr=False, n_streams=1, low_latency=False):
         self.in_rate = float(in_rate)
         self.out_rate = float(out_rate)
         self.ntype = int(ntype)
         self.channels = int(num_channels)
+        self.n_streams = int(n_streams)
         self.ended = False
         self._oi_ratio = self.out_rate / self.in_rate
         self._div_len = _div_len(self.in_rate, self.out_rate)
+        self._dtype = np.dtype(_DT_NAME[self.ntype])
+        self._fsz = self._dtype.itemsize * self.channels
         io = _lib.b200soxr_io_spec(self.ntype, self.ntype)
         qs = _lib.b200soxr_quality_spec(int(quality), 32 if vr else 0)
+        rt = _lib.b200soxr_runtime_spec(1)
+        if low_latency:
+            rt.flags |= RT_LOW_LATENCY
         err = C.c_char_p()
-        self._h = _lib.b200soxr_create(self.in_rate, self.out_rate, self.channels, C.byref(err),
-                                       C.byref(io), C.byref(qs), None)
+        if self.n_streams == 1:
+            self._h = _lib.b200soxr_create(self.in_rate, self.out_rate, self.channels, C.byref(err),
+                                           C.byref(io), C.byref(qs), C.byref(rt))
+        else:
+            self._h = _lib.b200soxr_create_batch(self.in_rate, self.out_rate, self.n_streams, self.channels,
+                                                 C.byref(err), C.byref(io), C.byref(qs), C.byref(rt))
         if err.value:
             self._h = None
             raise RuntimeError(err.value.decode())
+        self._odone = C.c_size_t(0)
+        self._odone_ref = C.byref(self._odone)
 
-    def __del__(self):
+    def __del__(self, _delete=_lib.b200soxr_delete):   # (bound at definition: module globals may be gone at exit)
         h = getattr(self, "_h", None)
         if h:
-            _lib.b200soxr_delete(h)
+            _delete(h)
             self._h = None
 
     def _process(self, x, last, code):
-        if type(x) is not np.ndarray or x.ndim != 2:
-            raise TypeError("process(): incompatible function arguments (need a 2-D ndarray)")
+        B = self.n_streams
+        if type(x) is not np.ndarray or x.ndim != (2 if B == 1 else 3):
+            raise TypeError("process(): incompatible function arguments (need a %d-D ndarray)" % (2 if B == 1 else 3))
         if self.ended:
             raise RuntimeError("Input after last input")
-        if x.shape[1] != self.channels:
+        if x.shape[-1] != self.channels or (B > 1 and x.shape[0] != B):
             raise ValueError("Channel num mismatch")
-        if code != self.ntype or _DT_CODE.get(x.dtype) != code:
+        if code != self.ntype or x.dtype != self._dtype:
             raise TypeError("Data type mismatch")
-        x = np.ascontiguousarray(x)
-        ilen, ch = x.shape
-        fsz = x.itemsize * ch
+        if not x.flags.c_contiguous:
+            x = np.ascontiguousarray(x)
+        ilen = x.shape[-2]
+        fsz = self._fsz
+        h = self._h
+        process = _lib.b200soxr_process
         x_addr = x.__array_interface__['data'][0]      # (ndarray.ctypes builds a helper object per access: 3x slower)
         # lowest-latency sizing of the reference (soxr_ext.cpp:155-158)
-        olen = int(_lib.b200soxr_delay(self._h) + ilen * self._oi_ratio + 1)
-        y = np.empty((max(olen, 1), ch), dtype=x.dtype)
+        olen = int(_lib.b200soxr_delay(h) + ilen * self._oi_ratio + 1)
+        odone = self._odone
+        if B > 1:
+            return self._process_batch(x, x_addr, ilen, olen, last)
+        y = np.empty((max(olen, 1), self.channels), dtype=self._dtype)
         y_addr = y.__array_interface__['data'][0]
         out_pos = 0
-        odone = C.c_size_t(0)
         for idx in range(0, ilen, self._div_len):
-            err = _lib.b200soxr_process(self._h, x_addr + idx * fsz, min(self._div_len, ilen - idx), None,
-                                        y_addr + out_pos * fsz, olen - out_pos, C.byref(odone))
+            err = process(h, x_addr + idx * fsz, min(self._div_len, ilen - idx), None,
+                          y_addr + out_pos * fsz, olen - out_pos, self._odone_ref)
             if err:
                 raise RuntimeError(err.decode())
             out_pos += odone.value
@@ -250,17 +276,44 @@ class CSoxr:
             self.ended = True
             while True:       # flush until no more output (soxr_ext.cpp:109-127)
                 if olen <= out_pos:
-                    y = np.concatenate([y[:out_pos], np.empty((max(olen, 1024), ch), dtype=x.dtype)])
+                    y = np.concatenate([y[:out_pos], np.empty((max(olen, 1024), self.channels), dtype=self._dtype)])
                     y_addr = y.__array_interface__['data'][0]
                     olen = y.shape[0]
-                err = _lib.b200soxr_process(self._h, None, 0, None,
-                                            y_addr + out_pos * fsz, olen - out_pos, C.byref(odone))
+                err = process(h, None, 0, None, y_addr + out_pos * fsz, olen - out_pos, self._odone_ref)
                 if err:
                     raise RuntimeError(err.decode())
                 out_pos += odone.value
                 if odone.value == 0:
                     break
-        return y[:out_pos].copy()
+        return y[:out_pos]      # a fresh array per call (the reference copies out of its reusable buffer, soxr_ext.cpp:187)
+
+    def _process_batch(self, x, x_addr, ilen, olen, last):
+        """n_streams > 1: one b200soxr_process call per chunk (and per flush round); the library packs the result
+        as [stream][odone][channel], so every call's piece is a view of the flat buffer it was written into."""
+        B, ch, h = self.n_streams, self.channels, self._h
+        odone = self._odone
+        pieces = []
+        if ilen:
+            buf = np.empty(B * max(olen, 1) * ch, dtype=self._dtype)
+            err = _lib.b200soxr_process(h, x_addr, ilen, None, buf.__array_interface__['data'][0], olen,
+                                        self._odone_ref)
+            if err:
+                raise RuntimeError(err.decode())
+            pieces.append(buf[:B * odone.value * ch].reshape(B, odone.value, ch))
+        if last:
+            self.ended = True
+            while True:
+                cap = max(olen, 1024)
+                buf = np.empty(B * cap * ch, dtype=self._dtype)
+                err = _lib.b200soxr_process(h, None, 0, None, buf.__array_interface__['data'][0], cap, self._odone_ref)
+                if err:
+                    raise RuntimeError(err.decode())
+                if odone.value == 0:
+                    break
+                pieces.append(buf[:B * odone.value * ch].reshape(B, odone.value, ch))
+        if not pieces:
+            return np.empty((B, 0, ch), dtype=self._dtype)
+        return pieces[0] if len(pieces) == 1 else np.concatenate(pieces, axis=1)
 
     def process_float32(self, x, last=False): return self._process(x, last, 0)
     def process_float64(self, x, last=False): return self._process(x, last, 1)

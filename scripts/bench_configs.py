@@ -147,6 +147,67 @@ if want("cfg3"):
                     ref_threads=1, rms_vs_ref=rms(y, yr) if y.shape == yr.shape else None)
     emit(**line)
 
+    # low-latency mode of the same stream (B200 extension): every call returns all output whose support has arrived
+    def run_ll():
+        rs = soxr.ResampleStream(44100, 16000, 8, dtype='float32', low_latency=True)
+        return np.concatenate([rs.resample_chunk(c, last=(i == len(chunks) - 1)) for i, c in enumerate(chunks)])
+    tb, tm = best(run_ll, n=3, warm=1)
+    yl = run_ll()
+    rs = soxr.ResampleStream(44100, 16000, 8, dtype='float32', low_latency=True)
+    first = [len(rs.resample_chunk(c)) for c in chunks[:4]]
+    emit(cfg="cfg3-lowlat", what="same stream, low_latency=True", gpu_us_per_chunk=tb / len(chunks) * 1e6,
+         first_call_counts=first, delay_after_4_chunks=rs.delay(), rms_vs_default_mode=rms(yl, y))
+
+    # many streams through one handle (ResampleStreamBatch): B x 8 ch, 1024-frame chunks, one launch per chunk.
+    # Chunks are laid out [chunk][stream][frame][channel] so each call's input is contiguous (as it would arrive);
+    # "pinned": the chunk arrays live in page-locked memory (torch pin_memory), so the H2D copy is a true DMA.
+    for B, pinned in ((16, False), (64, False), (256, False), (256, True)):
+        nb = 60
+        src = np.random.default_rng(5).standard_normal((nb, B, 1024, 8)).astype(np.float32)
+        if pinned:
+            keep = torch.from_numpy(src).pin_memory()
+            xb = keep.numpy()
+        else:
+            xb = src
+
+        def run_batch():
+            rs = soxr.ResampleStreamBatch(44100, 16000, B, 8, dtype='float32')
+            n = 0
+            for i in range(nb):
+                n += rs.resample_chunk(xb[i], last=(i == nb - 1)).shape[1]
+            return n
+        tb, tm = best(run_batch, n=3, warm=1)
+        line = dict(cfg="cfg3-batch", what="%d streams x 8 ch f32 44.1k->16k HQ through one handle, %d chunks of 1024 frames each, %s host numpy"
+                    % (B, nb, "pinned" if pinned else "pageable"),
+                    gpu_us_per_call=tb / nb * 1e6, gpu_us_per_stream_chunk=tb / nb / B * 1e6,
+                    gpu_stream_chunks_per_s=nb * B / tb, gpu_msamples_s=xb.size / tb / 1e6)
+        if have_ref:
+            line.update(ref_stream_chunks_per_s_one_thread=len(chunks) / rb, ref_threads=1,
+                        speedup_vs_one_ref_thread=(nb * B / tb) / (len(chunks) / rb), host_cores=cores)
+        emit(**line)
+    # the same 256 streams with device-resident chunks (RT_DEVICE_IO through the C ABI): what the kernels sustain
+    import ctypes as C
+    L = soxr.soxr_ext._lib
+    B, nb = 256, 60
+    io = L.b200soxr_io_spec(0, 0); qs = L.b200soxr_quality_spec(4, 0); rt = L.b200soxr_runtime_spec(1)
+    rt.flags |= soxr.soxr_ext.RT_DEVICE_IO
+    err = C.c_char_p()
+    h = L.b200soxr_create_batch(44100.0, 16000.0, B, 8, C.byref(err), C.byref(io), C.byref(qs), C.byref(rt))
+    xd = torch.randn((nb, B, 1024, 8), device=dev)
+    yd = torch.empty((B, 2048, 8), device=dev)
+    od = C.c_size_t(0)
+
+    def run_dev():
+        L.b200soxr_clear(h)
+        for i in range(nb):
+            L.b200soxr_process(h, xd[i].data_ptr(), 1024, None, yd.data_ptr(), 2048, C.byref(od))
+        torch.cuda.synchronize()
+    tb, tm = best(run_dev, n=3, warm=1)
+    L.b200soxr_delete(h)
+    emit(cfg="cfg3-batch-device", what="256 streams x 8 ch, device-resident chunks (B200SOXR_RT_DEVICE_IO), %d chunks" % nb,
+         gpu_us_per_call=tb / nb * 1e6, gpu_stream_chunks_per_s=nb * B / tb, gpu_msamples_s=xd.numel() / tb / 1e6,
+         speedup_vs_one_ref_thread=((nb * B / tb) / (len(chunks) / rb)) if have_ref else None)
+
 # ---- cfg4 (one GPU's share of the 8-GPU config: 512 clips; and the whole 4096 on one GPU) -------------
 if want("cfg4"):
     for n_clips in (512, 4096):

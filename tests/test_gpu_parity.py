@@ -217,6 +217,83 @@ def test_stream_int(in_rate, out_rate, chunk_size, length, dtype):
     assert np.allclose(y_oneshot, y_stream, atol=2)
 
 
+@pytest.mark.parametrize('dtype,in_rate,out_rate,quality', [('float32', 44100, 16000, 'HQ'), ('float32', 48000, 44100, 'VHQ'),
+                                                            ('int16', 48000, 22050, 'HQ'), ('float64', 44100, 48000, 'VHQ'),
+                                                            ('float32', 44100, 47999.5, 'HQ')])
+def test_stream_batch_equals_separate_streams(dtype, in_rate, out_rate, quality):
+    # ResampleStreamBatch: B streams through ONE handle == B ResampleStreams, per call and bit for bit (ints incl. dither)
+    B, ch, chunk, n = 5, 2, 1024, 9000
+    scale = 5000.0 if np.dtype(dtype).kind == 'i' else 1.0
+    x = make_input(21, (B, n, ch), dtype, scale)
+    rb = soxr.ResampleStreamBatch(in_rate, out_rate, B, ch, dtype=dtype, quality=quality)
+    singles = [soxr.ResampleStream(in_rate, out_rate, ch, dtype=dtype, quality=quality) for _ in range(B)]
+    for i in range(0, n, chunk):
+        last = i + chunk >= n
+        yb = rb.resample_chunk(np.ascontiguousarray(x[:, i:i + chunk]), last=last)
+        assert yb.shape[0] == B and yb.shape[2] == ch
+        for b in range(B):
+            ys = singles[b].resample_chunk(x[b, i:i + chunk], last=last)
+            assert ys.shape == yb[b].shape
+            assert np.array_equal(ys, yb[b])
+        assert rb.delay() == singles[0].delay()
+    if np.dtype(dtype).kind == 'i':
+        assert rb.num_clips() == sum(s.num_clips() for s in singles)
+    rb.clear()
+    y2 = rb.resample_chunk(np.ascontiguousarray(x[:, :3000]), last=True)
+    s2 = soxr.ResampleStream(in_rate, out_rate, ch, dtype=dtype, quality=quality)
+    if np.dtype(dtype).kind != 'i':   # (after clear() the reference restarts the dither seed from 0, not from its create-time value)
+        assert np.array_equal(y2[3], s2.resample_chunk(x[3, :3000], last=True))
+    with pytest.raises(ValueError):
+        soxr.ResampleStreamBatch(in_rate, out_rate, B, ch, dtype=dtype).resample_chunk(x[:2, :100])
+
+
+def test_stream_history_moves_from_host_to_device_on_a_large_chunk():
+    # small chunks keep their history in mapped pinned host memory; the first chunk above the zero-copy size moves it
+    # to the device for good.  The result must not depend on where the history lives.
+    x = np.random.default_rng(31).standard_normal((300000, 2)).astype(np.float32)
+    want = soxr._resample_oneshot(x, 44100, 32000)
+    rs = soxr.ResampleStream(44100, 32000, 2, dtype='float32')
+    cuts = [0, 700, 1724, 2000, 2000 + 40000, 2000 + 40000 + 300, 180000, 180017, 300000]   # 40000 x 2 x 4 B = 320 kB > 256 kB
+    ys = [rs.resample_chunk(x[a:b], last=(b == 300000)) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert np.array_equal(np.concatenate(ys), want)
+
+
+@pytest.mark.parametrize('in_rate,out_rate,quality,dtype', [(44100, 16000, 'HQ', 'float32'), (48000, 44100, 'VHQ', 'float32'),
+                                                            (44100, 47999.5, 'VHQ', 'float64'), (48000, 8000, 'HQ', 'int16'),
+                                                            (16000, 44100, 'MQ', 'float32')])
+def test_low_latency_stream(in_rate, out_rate, quality, dtype):
+    # low_latency=True: every call returns all output whose filter support has arrived (direct-form kernels)
+    n, ch, chunk = 30000, 2, 1024
+    scale = 5000.0 if np.dtype(dtype).kind == 'i' else 1.0
+    x = make_input(41, (n, ch), dtype, scale)
+    want = O.resample_f64(x, in_rate, out_rate, Q[quality])
+    rs = soxr.ResampleStream(in_rate, out_rate, ch, dtype=dtype, quality=quality, low_latency=True)
+    ref_mode = soxr.ResampleStream(in_rate, out_rate, ch, dtype=dtype, quality=quality)
+    ys, got_total, fed = [], 0, 0
+    for i in range(0, n, chunk):
+        last = i + chunk >= n
+        y = rs.resample_chunk(x[i:i + chunk], last=last)
+        ref_mode.resample_chunk(x[i:i + chunk], last=last)
+        fed = min(n, i + chunk)
+        got_total += len(y)
+        ys.append(y)
+        if not last:
+            # pending output = what the zero-phase filters still wait for: well under the reference's FFT-block latency
+            assert abs(rs.delay() - (fed * out_rate / in_rate - got_total)) < 1e-6
+            assert rs.delay() < 700 * max(1.0, out_rate / in_rate)
+            assert rs.delay() <= ref_mode.delay() + 1e-9 or ref_mode.delay() < 1
+    y = np.concatenate(ys)
+    assert y.shape == want.shape and rs.delay() == 0
+    if np.dtype(dtype).kind == 'i':
+        assert np.abs(y - want).max() <= 1.5 + 1e-3 * np.abs(want).max()
+    else:
+        assert rms(y.astype(np.float64) - want) <= (TOL_F64 if dtype == 'float64' and quality == 'VHQ' else TOL_F32)
+    # independent of the chunking (position-keyed direct form), so also equal to one big chunk
+    rs2 = soxr.ResampleStream(in_rate, out_rate, ch, dtype=dtype, quality=quality, low_latency=True)
+    if np.dtype(dtype).kind != 'i':
+        assert np.array_equal(rs2.resample_chunk(x, last=True), y)
+
+
 def test_stream_clear_resets_clip_counter_int16():
     # soxr_clear zeroes the clip counter (soxr.c:609-628); the device-side accumulator must follow
     x = np.where(np.sin(2 * np.pi * np.arange(4000) / 100.0) >= 0, 32767, -32768).astype(np.int16)[:, None]
