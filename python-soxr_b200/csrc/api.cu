@@ -805,26 +805,61 @@ b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *d, void co
       B2_CUDA(cudaEventRecord(ev_start, st));          // order after earlier work queued on st
       B2_CUDA(cudaStreamWaitEvent(ws->h2d_stream, ev_start, 0));
       B2_CUDA(cudaStreamWaitEvent(ws->d2h_stream, ev_start, 0));
+      // Pageable caller memory (an ordinary ndarray: the drop-in case) cannot be DMA'd directly; the driver's own
+      // staging runs at a fraction of the link.  Such chunks go through three pinned staging slots per direction,
+      // filled / drained by the host copy pool while the copy engines and the kernels work on the other slots.
+      auto pageable = [](const void *ptr) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, ptr) != cudaSuccess) { cudaGetLastError(); return true; }
+        return pa.type == cudaMemoryTypeUnregistered;
+      };
+      static const bool no_staging = [] { const char *v = std::getenv("B200SOXR_NO_HOST_STAGING"); return v && v[0] == '1'; }();
+      const bool stage_in = !no_staging && pageable(in), stage_out = !no_staging && pageable(out);
+      constexpr unsigned kSlots = 3;
+      struct Pending { size_t ooff, obytes; unsigned slot; };
+      std::vector<Pending> pend(n_chunks);
+      auto sync_all = [&] { cudaStreamSynchronize(ws->h2d_stream); cudaStreamSynchronize(st); cudaStreamSynchronize(ws->d2h_stream); };
+      auto drain = [&](unsigned c) -> const char * {      // chunk c's result: staging slot -> caller memory
+        B2_CUDA(cudaEventSynchronize(ws->events[2 * c + 1]));
+        if (stage_out) parallel_memcpy(static_cast<char *>(out) + pend[c].ooff, ws->pin_ring_out[pend[c].slot].p, pend[c].obytes);
+        return nullptr;
+      };
       for (unsigned c = 0; c < n_chunks; ++c) {
-        const unsigned c0 = c * per_chunk, nc = std::min(per_chunk, d->n_clips - c0);
+        const unsigned c0 = c * per_chunk, nc = std::min(per_chunk, d->n_clips - c0), slot = c % kSlots;
         IoLayout l1 = li, l2 = lo;
         l1.n_clips = l2.n_clips = nc;
         const size_t ispan = span(l1, d->ilen), ospan = span(l2, total);
         const size_t ioff = size_t(c0) * size_t(d->in_clip_stride) * isz, ooff = size_t(c0) * size_t(d->out_clip_stride) * isz;
-        B2_CUDA(cudaMemcpyAsync(static_cast<char *>(ws->in_stage.p) + ioff, static_cast<const char *>(in) + ioff,
-                                ispan * isz, cudaMemcpyHostToDevice, ws->h2d_stream));
+        pend[c] = Pending{ooff, ospan * isz, slot};
+        // the slot's previous tenant (chunk c - kSlots) must have left: its D2H done and copied out
+        if ((stage_in || stage_out) && c >= kSlots)
+          if ((e = drain(c - kSlots))) { sync_all(); return e; }
+        const void *h2d_src = static_cast<const char *>(in) + ioff;
+        if (stage_in) {
+          if ((e = ws->pin_ring_in[slot].reserve(ispan * isz))) { sync_all(); return e; }
+          parallel_memcpy(ws->pin_ring_in[slot].p, h2d_src, ispan * isz);
+          h2d_src = ws->pin_ring_in[slot].p;
+        }
+        B2_CUDA(cudaMemcpyAsync(static_cast<char *>(ws->in_stage.p) + ioff, h2d_src, ispan * isz, cudaMemcpyHostToDevice,
+                                ws->h2d_stream));
         B2_CUDA(cudaEventRecord(ws->events[2 * c], ws->h2d_stream));
         B2_CUDA(cudaStreamWaitEvent(st, ws->events[2 * c], 0));
         B2_CUDA(cudaMemsetAsync(static_cast<char *>(ws->out_stage.p) + ooff, 0, ospan * isz, st));
-        if ((e = compute(c0, nc, ws->in_stage.p, ws->out_stage.p))) {
-          cudaStreamSynchronize(ws->h2d_stream); cudaStreamSynchronize(st); cudaStreamSynchronize(ws->d2h_stream);
-          return e;
-        }
+        if ((e = compute(c0, nc, ws->in_stage.p, ws->out_stage.p))) { sync_all(); return e; }
         B2_CUDA(cudaEventRecord(ws->events[2 * c + 1], st));
         B2_CUDA(cudaStreamWaitEvent(ws->d2h_stream, ws->events[2 * c + 1], 0));
-        B2_CUDA(cudaMemcpyAsync(static_cast<char *>(out) + ooff, static_cast<char *>(ws->out_stage.p) + ooff, ospan * isz,
-                                cudaMemcpyDeviceToHost, ws->d2h_stream));
+        void *d2h_dst = static_cast<char *>(out) + ooff;
+        if (stage_out) {
+          if ((e = ws->pin_ring_out[slot].reserve(ospan * isz))) { sync_all(); return e; }
+          d2h_dst = ws->pin_ring_out[slot].p;
+        }
+        B2_CUDA(cudaMemcpyAsync(d2h_dst, static_cast<char *>(ws->out_stage.p) + ooff, ospan * isz, cudaMemcpyDeviceToHost,
+                                ws->d2h_stream));
+        B2_CUDA(cudaEventRecord(ws->events[2 * c + 1], ws->d2h_stream));   // re-recorded: now marks the end of the D2H
       }
+      if (stage_in || stage_out)
+        for (unsigned c = n_chunks > kSlots ? n_chunks - kSlots : 0; c < n_chunks; ++c)
+          if ((e = drain(c))) { sync_all(); return e; }
       B2_CUDA(cudaStreamSynchronize(ws->d2h_stream));
     }
   }

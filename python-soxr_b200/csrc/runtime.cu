@@ -2,8 +2,11 @@
 #include "runtime.h"
 
 #include <algorithm>
+#include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <map>
+#include <thread>
 
 #include "fdr_stage.cuh"
 #include "fft_stage.cuh"
@@ -54,6 +57,8 @@ DevicePlan::~DevicePlan() {
 Workspace::~Workspace() {
   for (DevBuf *b : {&in_stage, &out_stage, &x, &y, &t0, &t1, &seeds, &blocks, &misc}) b->release();
   for (PinnedBuf *b : {&pin_in, &pin_out, &pin_misc}) b->release();
+  for (PinnedBuf &b : pin_ring_in) b.release();
+  for (PinnedBuf &b : pin_ring_out) b.release();
   if (stream) cudaStreamDestroy(stream);
   if (h2d_stream) cudaStreamDestroy(h2d_stream);
   if (d2h_stream) cudaStreamDestroy(d2h_stream);
@@ -86,6 +91,73 @@ const char *Workspace::need_events(size_t n) {
     events.push_back(e);
   }
   return nullptr;
+}
+
+// ---- host copy pool ---------------------------------------------------------------------------------------
+namespace {
+class CopyPool {
+ public:
+  static CopyPool &get() {
+    static CopyPool *pool = new CopyPool();   // never destroyed: worker threads must not outlive their state at exit
+    return *pool;
+  }
+  void run(char *dst, const char *src, size_t bytes) {
+    const size_t kMin = size_t(1) << 20;
+    const unsigned parts = unsigned(std::min<size_t>(workers_.size() + 1, std::max<size_t>(1, bytes / kMin)));
+    if (parts <= 1) { std::memcpy(dst, src, bytes); return; }
+    const size_t per = ((bytes / parts) + 4095) & ~size_t(4095);
+    std::unique_lock<std::mutex> call_lock(call_mu_);        // one parallel copy at a time
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      dst_ = dst; src_ = src; bytes_ = bytes; per_ = per; parts_ = parts; next_ = 1; pending_ = parts - 1;
+      ++generation_;
+    }
+    cv_.notify_all();
+    std::memcpy(dst, src, std::min(per, bytes));            // the caller takes part 0
+    std::unique_lock<std::mutex> l(mu_);
+    done_cv_.wait(l, [&] { return pending_ == 0; });
+  }
+
+ private:
+  CopyPool() {
+    unsigned n = std::thread::hardware_concurrency();
+    if (const char *e = std::getenv("B200SOXR_COPY_THREADS")) n = unsigned(std::max(1L, std::atol(e)));
+    else n = std::max(1u, std::min(8u, n / 2));
+    for (unsigned i = 1; i < n; ++i) workers_.emplace_back([this] { loop(); });
+    for (std::thread &t : workers_) t.detach();
+  }
+  void loop() {
+    unsigned long long seen = 0;
+    for (;;) {
+      unsigned part;
+      {
+        std::unique_lock<std::mutex> l(mu_);
+        cv_.wait(l, [&] { return generation_ != seen && next_ < parts_; });
+        part = next_++;
+        if (next_ >= parts_) seen = generation_;
+      }
+      const size_t off = size_t(part) * per_;
+      if (off < bytes_) std::memcpy(dst_ + off, src_ + off, std::min(per_, bytes_ - off));
+      {
+        std::lock_guard<std::mutex> l(mu_);
+        if (--pending_ == 0) done_cv_.notify_all();
+      }
+    }
+  }
+  std::mutex call_mu_, mu_;
+  std::condition_variable cv_, done_cv_;
+  std::vector<std::thread> workers_;
+  char *dst_ = nullptr;
+  const char *src_ = nullptr;
+  size_t bytes_ = 0, per_ = 0;
+  unsigned parts_ = 0, next_ = 0, pending_ = 0;
+  unsigned long long generation_ = 0;
+};
+}  // namespace
+
+void parallel_memcpy(void *dst, const void *src, size_t bytes) {
+  if (!bytes) return;
+  CopyPool::get().run(static_cast<char *>(dst), static_cast<const char *>(src), bytes);
 }
 
 namespace {

@@ -97,6 +97,7 @@ struct Workspace {
   const char *mark_busy(cudaStream_t st);
   DevBuf in_stage, out_stage, x, y, t0, t1, seeds, blocks, misc;
   PinnedBuf pin_in, pin_out, pin_misc;
+  PinnedBuf pin_ring_in[3], pin_ring_out[3];   // staging slots of the pageable-host batch pipeline
   // side stream for small kernels that may overlap the tail of a large one (k_fdr's head kernel), fenced by events
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t aux_ev[2] = {nullptr, nullptr};
@@ -107,6 +108,10 @@ struct Workspace {
 // order their own stream after Workspace::busy_ev instead)
 Workspace *acquire_workspace(bool host_wait = true);
 void release_workspace(Workspace *);
+
+// memcpy split over a small persistent pool of host threads (pageable <-> pinned staging of large batches: one
+// core moves ~10 GB/s, the PCIe link ~50 GB/s).  Blocks until the whole range is copied.
+void parallel_memcpy(void *dst, const void *src, size_t bytes);
 
 // User-side layout of a batch of clips.
 struct IoLayout {
