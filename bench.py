@@ -47,13 +47,37 @@ def _peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def _lib_sha():
+    import hashlib
+    try:
+        with open(os.path.join(ROOT, "python-soxr_b200", "soxr", "libb200soxr.so"), "rb") as f:
+            return hashlib.sha256(f.read()).hexdigest()[:16]
+    except OSError:
+        return None
+
+
 def _traffic():
-    """dram bytes per launch of the fused kernel from the committed ncu --set full capture, or None."""
+    """(dram bytes per launch of the dominant kernel, provenance).  ncu cannot run inside the timed region, so the
+    figure comes from the committed `ncu --set full` capture (profiles/latest_traffic.json); the provenance says
+    which build of the kernel source it was taken from, and whether that is the source this run was built from."""
+    import hashlib
     try:
         with open(os.path.join(ROOT, "profiles", "latest_traffic.json")) as f:
-            return json.load(f).get("dram_bytes_per_launch")
+            t = json.load(f)
     except Exception:
-        return None
+        return None, "no capture committed"
+    h = hashlib.sha256()
+    for name in ("fdr_stage.cuh", "fft_regs.cuh", "fdr_stage.cu"):
+        try:
+            with open(os.path.join(ROOT, "python-soxr_b200", "csrc", name), "rb") as f:
+                h.update(f.read())
+        except OSError:
+            pass
+    cur = h.hexdigest()[:16]
+    same = t.get("kernel_source_sha") == cur
+    src = "ncu --set full capture %s (kernel source sha %s; this run's source %s: %s)" % (
+        t.get("capture", "?"), t.get("kernel_source_sha", "?"), cur, "same" if same else "DIFFERENT - re-capture")
+    return t.get("dram_bytes_per_launch"), src
 
 
 class ClockSampler:
@@ -146,6 +170,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary (strong-scaling / gather / pageable) measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -263,6 +288,51 @@ def main():
         gather_ms = float(tg.item())
         del full
 
+    # ---- secondary measurements (BASELINE.json configs[1] and configs[3] as STRONG scaling: total work fixed) ----
+    def timed(fn, steps, warm=3):
+        for _ in range(warm):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(steps):
+            fn()
+        b.record(stream)
+        barrier()
+        tt = torch.tensor([a.elapsed_time(b) / steps], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    extra = {}
+    if not args.no_extra:
+        n_steps2 = max(3, min(args.steps, 10))
+        # cfg2, 1024 clips in TOTAL: every rank takes 1024 / N of them
+        n2 = N_CLIPS // world
+        ms = timed(lambda: soxr.resample_batch(x[:n2], IN_RATE, OUT_RATE, QUALITY, out=y[:n2], stream=stream.cuda_stream), n_steps2)
+        extra["strong_cfg2_1024_clips_total"] = {"clips_per_gpu": n2, "ms_per_step": ms,
+                                                 "value_msamples_s": N_CLIPS * FRAMES * CH / (ms * 1e-3) / 1e6}
+        # cfg4: int16 96000 -> 48000 HQ, 4096 mono clips in TOTAL, sharded over the ranks (512 per GPU at N = 8)
+        n4 = 4096 // world
+        x4 = (torch.randn((n4, 96000), device=dev, generator=gen) * 5000).round().to(torch.int16)
+        y4 = torch.empty((n4, 48000), dtype=torch.int16, device=dev)
+        ms4 = timed(lambda: soxr.resample_batch(x4, 96000, 48000, 'HQ', out=y4, stream=stream.cuda_stream), n_steps2)
+        alg4 = (x4.numel() + y4.numel()) * 2
+        extra["strong_cfg4_4096_int16_clips_total"] = {"clips_per_gpu": n4, "ms_per_step": ms4,
+                                                       "value_msamples_s": 4096 * 96000 / (ms4 * 1e-3) / 1e6,
+                                                       "achieved_gbs_per_gpu": alg4 / (ms4 * 1e-3) / 1e9}
+        del x4, y4
+        if dist is not None:
+            # resample + all_gather of the outputs, pipelined over sub-batches (soxr.distributed.resample_batch_gathered)
+            from soxr import distributed as sdist
+            msg = timed(lambda: sdist.resample_batch_gathered(x, IN_RATE, OUT_RATE, QUALITY, sub_batches=8), 3, warm=2)
+            recv = (world - 1) * N_CLIPS * out_frames * CH * 4
+            extra["weak_with_overlapped_all_gather"] = {
+                "ms_per_step": msg, "value_msamples_s": world * in_samples / (msg * 1e-3) / 1e6,
+                "bytes_received_per_gpu": recv, "link_gbs_per_gpu": recv / (msg * 1e-3) / 1e9,
+                "note": "every rank receives (N - 1) output shards: the step is bound by NVLink (measured peer copy 770 GB/s), "
+                        "not by the kernels; only the compute is hidden"}
+
     # sanity: the result is finite and has signal power (white noise through a unity-gain LPF)
     chk = float(y[:4].double().pow(2).mean().item())
     if not (0.5 < chk < 1.5):
@@ -295,6 +365,28 @@ def main():
                "h2d_bytes_per_step": int(xh.numel() * 4), "d2h_bytes_per_step": int(yh.numel() * 4),
                "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3,
                "api": "soxr.resample_batch(numpy) -> b200soxr_resample_batch, pinned host buffers"}
+        if not args.no_extra:
+            # the same call with ordinary (pageable) ndarrays: the library stages them through pinned slots itself
+            xp = np.empty(xn.shape, np.float32)
+            xp[...] = xn
+            yp = np.empty(yn.shape, np.float32)
+            for _ in range(2):
+                soxr.resample_batch(xp, IN_RATE, OUT_RATE, QUALITY, out=yp)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                soxr.resample_batch(xp, IN_RATE, OUT_RATE, QUALITY, out=yp)
+            dtp = time.perf_counter() - t0
+            tp = torch.tensor([dtp], dtype=torch.float64, device=dev)
+            if dist is not None:
+                dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+            dtp = float(tp.item())
+            if not np.array_equal(yp[5, :256], yn[5, :256]):
+                raise SystemExit("bench.py: pageable host path disagrees with the pinned one")
+            e2e["pageable"] = {"value": world * in_samples * n_e2e / dtp / 1e6, "ms_per_step": dtp / n_e2e * 1e3,
+                               "slowdown_vs_pinned": dtp / dt,
+                               "api": "the same call with ordinary (pageable) numpy arrays"}
+            del xp, yp
         del xh, yh
 
     if rank != 0:
@@ -303,6 +395,7 @@ def main():
         return 0
 
     peak, peak_src = _peaks()
+    traffic, traffic_src = _traffic()
     alg_bytes = (N_CLIPS * FRAMES * CH + N_CLIPS * out_frames * CH) * 4
     k_ms = sorted(kernel_ms)
     k_avg = sum(kernel_ms) / len(kernel_ms)
@@ -316,9 +409,9 @@ def main():
                    "l2": "inputs (393 MB) + outputs (361 MB) per step exceed the 126 MB L2; no explicit flush",
                    "output_msamples_per_s": value * out_frames / FRAMES,
                    "sharding": "clips split contiguously over ranks, no data-path collective",
-                   "final_all_gather_ms": gather_ms, "cpu_affinity": numa},
+                   "final_all_gather_ms": gather_ms, "cpu_affinity": numa, "secondary": extra or None},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": _traffic(), "kernel": KERNEL_DESC,
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel": KERNEL_DESC, "library_sha256_16": _lib_sha(),
                      "kernel_ms_avg": k_avg, "kernel_ms_min": k_ms[0], "kernel_ms_median": k_ms[len(k_ms) // 2],
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                      "note": "kernel_ms_* = CUDA-event time of one whole step (all its launches) on the launching stream; "

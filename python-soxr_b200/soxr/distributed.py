@@ -15,7 +15,9 @@ A single stream (ResampleStream) does not shard: replicas only.
     y_local = resample_shard(x[lo:hi], 48000, 44100, 'VHQ')
     y = gather_shards(y_local, n_clips, dst=None)        # every rank gets [n_clips, frames, ch]
 
-or in one call `resample_batch_sharded(x_full_or_local, ...)`.
+or in one call `resample_batch_sharded(x_full_or_local, ...)`.  `resample_batch_gathered` is the pipelined form of
+resample + all_gather: the shard is cut into sub-batches and the gather of sub-batch i runs on a side stream while
+sub-batch i + 1 is being resampled.
 """
 import numpy as np
 
@@ -131,3 +133,53 @@ def resample_batch_sharded(x, in_rate, out_rate, quality='HQ', gather=None, x_is
     if gather is None:
         return y_local
     return gather_shards(y_local, n_clips, dst=None if gather == 'all' else int(gather), group=group)
+
+
+def resample_batch_gathered(x_local, in_rate, out_rate, quality='HQ', sub_batches=4, group=None, _compute=None):
+    """Resample this rank's clips and all_gather the outputs, overlapped: every rank returns [world * n_local, ...].
+
+    The local shard (torch tensor; equal size on every rank) is processed in `sub_batches` pieces.  Each piece is
+    written straight into its final place in the gathered result, and its all_gather is queued behind it on a side
+    stream while the next piece is computed, so only the last piece's gather is exposed behind the compute (the
+    gather itself is bound by the link: every rank receives (world - 1) shards).
+    """
+    import torch
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n_local = int(x_local.shape[0])
+    sizes = torch.tensor([n_local], dtype=torch.int64, device=x_local.device)
+    lo_hi = torch.stack([sizes.clone(), -sizes.clone()])
+    dist.all_reduce(lo_hi, op=dist.ReduceOp.MAX, group=group)
+    if int(lo_hi[0].item()) != n_local or int(-lo_hi[1].item()) != n_local:
+        raise ValueError('resample_batch_gathered needs equal shards on every rank (use gather_shards for ragged ones)')
+    total = soxr_ext.output_frames(in_rate, out_rate, int(x_local.shape[1]))
+    tail = (total,) + tuple(x_local.shape[2:])
+    full = x_local.new_empty((world * n_local,) + tail)
+    if n_local == 0:
+        return full
+    cuda = x_local.is_cuda
+    sub_batches = max(1, min(int(sub_batches), n_local))
+    bounds = [shard_bounds(n_local, sub_batches, j) for j in range(sub_batches)]
+    comm = torch.cuda.Stream(device=x_local.device) if cuda else None
+    works = []
+    for lo, hi in bounds:
+        y_j = full[rank * n_local + lo:rank * n_local + hi]
+        if _compute is not None:
+            y_j.copy_(torch.as_tensor(_compute(x_local[lo:hi], in_rate, out_rate, quality)))
+        else:
+            from . import resample_batch
+            resample_batch(x_local[lo:hi], in_rate, out_rate, quality, out=y_j)
+        outs = [full[r * n_local + lo:r * n_local + hi] for r in range(world)]
+        if cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(comm):
+                comm.wait_event(ev)          # the collective starts when THIS piece is done, not the whole shard
+                works.append(dist.all_gather(outs, y_j, group=group, async_op=True))
+        else:
+            works.append(dist.all_gather(outs, y_j.clone(), group=group, async_op=True))
+    for w in works:
+        w.wait()
+    if cuda:
+        torch.cuda.current_stream(x_local.device).wait_stream(comm)
+    return full

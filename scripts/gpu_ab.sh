@@ -6,7 +6,7 @@ cp $LIB /tmp/orig.so
 for v in scratch/variants/*.so; do
   n=$(basename $v .so)
   cp $v $LIB
-  python bench.py --steps 30 --warmup 5 --no-e2e --no-cpu-baseline 2>&1 | tail -1 | python -c "
+  python bench.py --steps 30 --warmup 5 --no-e2e --no-cpu-baseline --no-extra 2>&1 | tail -1 | python -c "
 import json,sys
 l=sys.stdin.read()
 try:

@@ -5,8 +5,8 @@ TAG=${1:-p}
 OUT=gpurun_out
 mkdir -p $OUT
 python scratch/gpu_check.py 2>&1 | tee $OUT/${TAG}_check.log
-python bench.py --steps 30 --warmup 5 --no-e2e --no-cpu-baseline 2>&1 | tail -1 | tee $OUT/${TAG}_bench.json
+python bench.py --steps 30 --warmup 5 --no-e2e --no-cpu-baseline --no-extra 2>&1 | tail -1 | tee $OUT/${TAG}_bench.json
 if [ "$2" != "noprof" ]; then
 ncu --set full --clock-control none --import-source on -k regex:"k_fdr|k_fft_stage" -s 3 -c 2 -f -o $OUT/${TAG}_prof \
-    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-extra > $OUT/${TAG}_ncu_full.log 2>&1
 fi

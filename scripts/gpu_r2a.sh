@@ -7,5 +7,5 @@ rm -f $OUT/ab.log
 bash scripts/gpu_ab.sh check
 cp $OUT/ab.log $OUT/r2a_ab.log
 ncu --set full --clock-control none --import-source on -k regex:"k_fdr" -s 3 -c 2 -f -o $OUT/r2a_prof \
-    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/r2a_ncu_full.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-extra > $OUT/r2a_ncu_full.log 2>&1
 ls -la $OUT | tail -5

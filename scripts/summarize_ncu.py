@@ -84,5 +84,12 @@ if h is not None:
 open(out, 'w').write("\n".join(lines) + "\n")
 if traffic:
     with open(os.path.join(os.path.dirname(out), 'latest_traffic.json'), 'w') as f:
-        json.dump({"dram_bytes_per_launch": traffic, "kernel": traffic_kernel[:80], "source": os.path.basename(out)}, f)
+        import hashlib
+        h = hashlib.sha256()
+        csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "python-soxr_b200", "csrc")
+        for name in ("fdr_stage.cuh", "fft_regs.cuh", "fdr_stage.cu"):   # what bench.py hashes: run this right after the capture
+            with open(os.path.join(csrc, name), "rb") as g:
+                h.update(g.read())
+        json.dump({"dram_bytes_per_launch": traffic, "kernel": traffic_kernel[:80], "source": os.path.basename(out),
+                   "capture": os.path.basename(rep), "kernel_source_sha": h.hexdigest()[:16]}, f)
 print("\n".join(lines[:40]))

@@ -73,6 +73,16 @@ def _gloo_worker(rank, world, port, n_clips, channels, out_dir):
         np.save(os.path.join(out_dir, "local_%d.npy" % rank), y_local)
         if y_root is not None:
             np.save(os.path.join(out_dir, "root.npy"), y_root)
+        # 4. pipelined resample + all_gather (equal shards only): sub-batches gathered while the next one is computed
+        if n_clips % world == 0:
+            import torch
+            y_pipe = DD.resample_batch_gathered(torch.from_numpy(x[lo:hi]), 48000, 44100, 'HQ', sub_batches=2,
+                                                _compute=_oracle_compute)
+            np.save(os.path.join(out_dir, "pipe_%d.npy" % rank), y_pipe.numpy())
+        else:
+            import torch
+            with pytest.raises(ValueError):
+                DD.resample_batch_gathered(torch.from_numpy(x[lo:hi]), 48000, 44100, 'HQ', _compute=_oracle_compute)
         # a shard that does not follow shard_bounds() is refused
         if world == 2 and n_clips == 5:
             bad = x[:1] if rank == 0 else x[1:]
@@ -82,7 +92,7 @@ def _gloo_worker(rank, world, port, n_clips, channels, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n_clips,channels", [(2, 4, 2), (2, 5, 0), (3, 2, 1), (3, 7, 2)])
+@pytest.mark.parametrize("world,n_clips,channels", [(2, 4, 2), (2, 5, 0), (3, 2, 1), (3, 7, 2), (3, 6, 1)])
 def test_sharded_batch_matches_single_process_gloo(tmp_path, world, n_clips, channels):
     import torch.multiprocessing as mp
     port = _free_port()
@@ -95,6 +105,8 @@ def test_sharded_batch_matches_single_process_gloo(tmp_path, world, n_clips, cha
         assert got.shape == want.shape and np.array_equal(got, want)
         lo, hi = D.shard_bounds(n_clips, world, r)
         assert np.array_equal(np.load(tmp_path / ("local_%d.npy" % r)), want[lo:hi])
+        if n_clips % world == 0:
+            assert np.array_equal(np.load(tmp_path / ("pipe_%d.npy" % r)), want)
     assert np.array_equal(np.load(tmp_path / "root.npy"), want)
 
 
@@ -128,6 +140,11 @@ def _nccl_worker(rank, world, port, out_dir):
         assert torch.equal(y_all, y_one)            # a clip's result does not depend on its batch neighbours
         lo, hi = DD.shard_bounds(n_clips, world, rank)
         y_loc = DD.resample_batch_sharded(x[lo:hi].contiguous(), 48000, 44100, 'VHQ', gather=0, x_is_local=True)
+        # pipelined resample + all_gather on equal shards: sub-batch gathers overlap the next sub-batch's kernels
+        xe = x[:6 * world]
+        y_pipe = DD.resample_batch_gathered(xe[6 * rank:6 * rank + 6].contiguous(), 48000, 44100, 'VHQ', sub_batches=3)
+        torch.cuda.synchronize()
+        assert torch.equal(y_pipe, y_one[:6 * world])
         if rank == 0:
             assert torch.equal(y_loc, y_one)
             np.save(os.path.join(out_dir, "y.npy"), y_one[:2].cpu().numpy())
