@@ -312,7 +312,7 @@ const char *prepare_cfg(DevicePlan *dp, int variant) {
 }
 
 template <class Cfg, bool FAST>
-const char *launch_cfg_t(const FdrInfo &fi, const FdrKParams &P, long long n_items, cudaStream_t st) {
+const char *launch_cfg_t(const FdrInfo &fi, FdrKParams P, long long n_items, cudaStream_t st, Workspace *ws) {
   auto kern = k_fdr<Cfg, FAST>;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -343,14 +343,40 @@ const char *launch_cfg_t(const FdrInfo &fi, const FdrKParams &P, long long n_ite
     dc = c;
   }
   const long long grid = std::min<long long>(n_items, (long long)dc.sm_count * dc.per_sm);
+  // dynamic chunks when there is more than one item per CTA (about six chunks per CTA, at most 8 items each: the
+  // TMA staging of the next block works inside a chunk); the ticket counter lives in the caller's workspace
+  static const bool static_split = [] { const char *v = std::getenv("B200SOXR_FDR_STATIC_SPLIT"); return v && v[0] == '1'; }();
+  P.counter = nullptr;
+  P.ticket_base = P.n_chunks = P.n_big = 0;
+  P.chunk = P.chunk_tail = 1;
+  if (ws && !static_split && n_items > grid) {
+    if (!ws->fdr_tickets.p) {
+      if (const char *e = ws->fdr_tickets.reserve(sizeof(unsigned))) return e;
+      B2_CUDA(cudaMemsetAsync(ws->fdr_tickets.p, 0, sizeof(unsigned), st));
+      ws->fdr_ticket_base = 0;
+    }
+    auto env_long = [](const char *name, long dflt) { const char *v = std::getenv(name); return v ? std::atol(v) : dflt; };
+    static const long chunk_env = env_long("B200SOXR_FDR_CHUNK", 0), tail_pct = env_long("B200SOXR_FDR_TAIL_PCT", 25),
+                      tail_chunk = env_long("B200SOXR_FDR_TAIL_CHUNK", 2);
+    P.chunk = chunk_env > 0 ? unsigned(chunk_env)
+                            : unsigned(std::max<long long>(1, std::min<long long>(8, n_items / (grid * 4))));
+    P.chunk_tail = unsigned(std::max<long>(1, std::min<long>(tail_chunk, long(P.chunk))));
+    const long long tail_items = std::min<long long>(n_items, n_items * std::max(0L, std::min(100L, tail_pct)) / 100);
+    P.n_big = unsigned((n_items - tail_items) / P.chunk);
+    const long long rest = n_items - (long long)P.n_big * P.chunk;
+    P.n_chunks = P.n_big + unsigned((rest + P.chunk_tail - 1) / P.chunk_tail);
+    P.counter = ws->fdr_tickets.as<unsigned>();
+    P.ticket_base = ws->fdr_ticket_base;
+    ws->fdr_ticket_base += P.n_chunks + unsigned(grid);   // every CTA draws one ticket past the end
+  }
   kern<<<unsigned(grid), Cfg::THREADS, smem_bytes, st>>>(P);
   B2_COUNT_LAUNCH();
   B2_CUDA(cudaGetLastError());
   return nullptr;
 }
 template <class Cfg>
-const char *launch_cfg(const FdrInfo &fi, const FdrKParams &P, long long n_items, cudaStream_t st) {
-  return P.fast ? launch_cfg_t<Cfg, true>(fi, P, n_items, st) : launch_cfg_t<Cfg, false>(fi, P, n_items, st);
+const char *launch_cfg(const FdrInfo &fi, const FdrKParams &P, long long n_items, cudaStream_t st, Workspace *ws) {
+  return P.fast ? launch_cfg_t<Cfg, true>(fi, P, n_items, st, ws) : launch_cfg_t<Cfg, false>(fi, P, n_items, st, ws);
 }
 }  // namespace
 
@@ -390,7 +416,7 @@ const char *fdr_prepare(DevicePlan *dp) {
   return nullptr;
 }
 
-static const char *launch_variant(const FdrInfo &fi, const FdrKParams &P, long long n_items, cudaStream_t st);
+static const char *launch_variant(const FdrInfo &fi, const FdrKParams &P, long long n_items, cudaStream_t st, Workspace *ws);
 
 const char *fdr_run(const DevicePlan &dp, const FdrInfo &fi, const SigDesc &in, const SigDesc &out, long o0, long o1,
                     unsigned n_sig, unsigned group, cudaStream_t st, Workspace *ws) {
@@ -480,7 +506,7 @@ const char *fdr_run(const DevicePlan &dp, const FdrInfo &fi, const SigDesc &in, 
   P.itw2 = fi.itw.p;
   P.itw3 = static_cast<const char *>(fi.itw.p) + size_t(fi.itw3_off) * sizeof(float2);
   const long long n_items = (long long)P.n_pairs * P.n_blocks;
-  const char *err = launch_variant(fi, P, n_items, st);
+  const char *err = launch_variant(fi, P, n_items, st, ws);
   if (err) return err;
   if (head_after) {
     if (fi.n_head <= 32)
@@ -499,22 +525,22 @@ const char *fdr_run(const DevicePlan &dp, const FdrInfo &fi, const SigDesc &in, 
   return nullptr;
 }
 
-static const char *launch_variant(const FdrInfo &fi, const FdrKParams &P, long long n_items, cudaStream_t st) {
+static const char *launch_variant(const FdrInfo &fi, const FdrKParams &P, long long n_items, cudaStream_t st, Workspace *ws) {
   switch (fi.variant) {
-    case 1: return launch_cfg<FdrCfg160_147>(fi, P, n_items, st);
-    case 2: return launch_cfg<FdrCfg147_160>(fi, P, n_items, st);
-    case 3: return launch_cfg<FdrCfg2_1>(fi, P, n_items, st);
-    case 4: return launch_cfg<FdrCfg1_2>(fi, P, n_items, st);
-    case 5: return launch_cfg<FdrCfg2_1w>(fi, P, n_items, st);
-    case 6: return launch_cfg<FdrCfg3_1>(fi, P, n_items, st);
-    case 7: return launch_cfg<FdrCfg1_3>(fi, P, n_items, st);
-    case 8: return launch_cfg<FdrCfg441_160>(fi, P, n_items, st);
-    case 9: return launch_cfg<FdrCfg3_2>(fi, P, n_items, st);
-    case 10: return launch_cfg<FdrCfg2_3>(fi, P, n_items, st);
-    case 11: return launch_cfg<FdrCfg6_1>(fi, P, n_items, st);
-    case 12: return launch_cfg<FdrCfg1_6>(fi, P, n_items, st);
-    case 13: return launch_cfg<FdrCfg4_1>(fi, P, n_items, st);
-    case 14: return launch_cfg<FdrCfg1_4>(fi, P, n_items, st);
+    case 1: return launch_cfg<FdrCfg160_147>(fi, P, n_items, st, ws);
+    case 2: return launch_cfg<FdrCfg147_160>(fi, P, n_items, st, ws);
+    case 3: return launch_cfg<FdrCfg2_1>(fi, P, n_items, st, ws);
+    case 4: return launch_cfg<FdrCfg1_2>(fi, P, n_items, st, ws);
+    case 5: return launch_cfg<FdrCfg2_1w>(fi, P, n_items, st, ws);
+    case 6: return launch_cfg<FdrCfg3_1>(fi, P, n_items, st, ws);
+    case 7: return launch_cfg<FdrCfg1_3>(fi, P, n_items, st, ws);
+    case 8: return launch_cfg<FdrCfg441_160>(fi, P, n_items, st, ws);
+    case 9: return launch_cfg<FdrCfg3_2>(fi, P, n_items, st, ws);
+    case 10: return launch_cfg<FdrCfg2_3>(fi, P, n_items, st, ws);
+    case 11: return launch_cfg<FdrCfg6_1>(fi, P, n_items, st, ws);
+    case 12: return launch_cfg<FdrCfg1_6>(fi, P, n_items, st, ws);
+    case 13: return launch_cfg<FdrCfg4_1>(fi, P, n_items, st, ws);
+    case 14: return launch_cfg<FdrCfg1_4>(fi, P, n_items, st, ws);
   }
   return "internal: unknown fdr variant";
 }

@@ -322,6 +322,15 @@ struct FdrKParams {
   int n_blocks;                     // items per pair (block pairs when bpair)
   long o0, o1;
   const void *H, *ftw2, *ftw3, *itw2, *itw3;
+  // Dynamic work distribution: CTAs draw chunks of `chunk` consecutive (pair, block) items from a ticket counter
+  // (tickets of this launch start at ticket_base; the counter only ever counts up, so it needs no reset between
+  // launches).  With a static split the SM's warp arbiter lets some resident CTAs run ahead and finish early, and
+  // the others finish the launch with a fraction of the SM's warps (measured: 22 of 30 warps resident on average).
+  // counter == nullptr: static contiguous split.
+  // Guided: the first n_big tickets are chunks of `chunk` items (long runs keep the TMA staging of the next block
+  // going), the rest of the items are handed out in chunks of `chunk_tail` so the launch ends evenly.
+  unsigned *counter;
+  unsigned ticket_base, n_chunks, chunk, n_big, chunk_tail;
 };
 
 // first outputs of a two-stage cascade, direct form (see k_fdr_head)
@@ -357,11 +366,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
   // a contiguous range of (pair, block) items per CTA, walked incrementally: the per-pair address
   // set-up (integer divisions) runs only when the pair changes
   const unsigned long long n_items = (unsigned long long)P.n_pairs * unsigned(P.n_blocks);
-  const unsigned long long it0 = n_items * blockIdx.x / gridDim.x;
-  const int n_mine = int(n_items * (blockIdx.x + 1ull) / gridDim.x - it0);   // 32-bit loop state: registers are scarce
-  unsigned pair = unsigned(it0 / unsigned(P.n_blocks));
-  int bi = int(it0 % unsigned(P.n_blocks));
+  unsigned pair = 0;
+  int bi = 0, n_mine = 0;   // 32-bit loop state: registers are scarce
   bool fresh = true;
+  __shared__ unsigned s_ticket;
+  unsigned next_ticket = 0;   // thread 0: the ticket drawn ahead while the current chunk is processed
   // Per-pair state kept in registers across blocks: only what the interleaved-stereo fast path needs.  The other
   // layouts recompute their address set-up (pair_state) where they use it: at 64 registers per thread the full
   // state lived in local memory, and its reloads were 5 % of the warp stall samples (profiles/r1v).
@@ -401,9 +410,44 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
     mbar_init(&in_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
 #endif
+  if (tau == 0) s_ticket = P.counter ? atomicAdd(P.counter, 1u) - P.ticket_base : blockIdx.x;
+  __syncthreads();
+#ifdef B2_FDR_TIMING
+  // debug build (scripts/build_variant.sh -DB2_FDR_TIMING=1): per-CTA timeline printed by thread 0
+  unsigned long long dbg_t0 = 0;
+  long long dbg_edge = 0;
+  if (tau == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+  int dbg_n_edge = 0, dbg_items = 0;
+#endif
+  for (;;) {
+  {
+    const unsigned ticket = s_ticket;
+    unsigned long long it0;
+    if (P.counter) {
+      if (ticket >= P.n_chunks) break;
+      if (tau == 0) next_ticket = atomicAdd(P.counter, 1u) - P.ticket_base;
+      const bool big = ticket < P.n_big;
+      it0 = big ? (unsigned long long)ticket * P.chunk
+                : (unsigned long long)P.n_big * P.chunk + (unsigned long long)(ticket - P.n_big) * P.chunk_tail;
+      n_mine = int(min((unsigned long long)(big ? P.chunk : P.chunk_tail), n_items - it0));
+    } else {
+      if (ticket >= gridDim.x) break;
+      it0 = n_items * ticket / gridDim.x;
+      n_mine = int(n_items * (ticket + 1ull) / gridDim.x - it0);
+      next_ticket = gridDim.x;
+    }
+    pair = unsigned(it0 / unsigned(P.n_blocks));
+    bi = int(it0 % unsigned(P.n_blocks));
+    fresh = true;
+#if B2_FDR_TMA
+    staged = false;
+#endif
+  }
   for (int it = 0; it < n_mine; ++it) {
+#ifdef B2_FDR_TIMING
+    const long long dbg_b0 = tau == 0 ? clock64() : 0;
+#endif
     if (fresh) {
       const PairState ps = pair_state(pair);
       src_pair = reinterpret_cast<const float2 *>(static_cast<const float *>(ps.pin.p) + ps.pin.off0);
@@ -454,6 +498,14 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
         asm volatile("prefetch.global.L2 [%0];" ::"l"(src + Cfg::NIN + tau * 16));
 #endif
       FW::template fwd_p1<Cfg::TP_F1>(tau, bufA, [&](int g, int n) { return src[g + FW::G1 * n]; });
+    } else if (fast) {
+      // blocks that stick out of the clip (its first and last ones): the same float2 loads, zero outside [vlo, vhi)
+      const float2 *__restrict__ src = src_pair;
+      const long vlo = P.in.vlo, vhi = P.in.vhi;
+      FW::template fwd_p1<Cfg::TP_F1>(tau, bufA, [&](int g, int n) {
+        const long k = kb + g + FW::G1 * n;
+        return (k >= vlo && k < vhi) ? src[k] : make_float2(0.f, 0.f);
+      });
     } else {
       const PairIn<R> pin = pair_state(pair).pin;
       if (pin.vec && interior) {
@@ -569,12 +621,34 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
       bufA = bufB;
       bufB = t;
     }
+#ifdef B2_FDR_TIMING
+    if (!interior && tau == 0) {
+      dbg_edge += clock64() - dbg_b0;
+      ++dbg_n_edge;
+    }
+#endif
     if (++bi == P.n_blocks) {
       bi = 0;
       ++pair;
       fresh = true;
     }
   }
+#ifdef B2_FDR_TIMING
+  dbg_items += n_mine;
+#endif
+  // next chunk: its ticket was drawn at the start of this one (the atomic's latency is long gone)
+  if (tau == 0) s_ticket = next_ticket;
+  __syncthreads();
+  }
+#ifdef B2_FDR_TIMING
+  if (tau == 0) {
+    unsigned long long dbg_t1;
+    unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t1));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    printf("FDRT %u %u %llu %llu %d %d %lld\n", blockIdx.x, smid, dbg_t0, dbg_t1, dbg_items, dbg_n_edge, dbg_edge);
+  }
+#endif
 }
 #endif  // __CUDACC__
 

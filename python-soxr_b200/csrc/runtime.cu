@@ -55,7 +55,7 @@ DevicePlan::~DevicePlan() {
 }
 
 Workspace::~Workspace() {
-  for (DevBuf *b : {&in_stage, &out_stage, &x, &y, &t0, &t1, &seeds, &blocks, &misc}) b->release();
+  for (DevBuf *b : {&in_stage, &out_stage, &x, &y, &t0, &t1, &seeds, &blocks, &misc, &fdr_tickets}) b->release();
   for (PinnedBuf *b : {&pin_in, &pin_out, &pin_misc}) b->release();
   for (PinnedBuf &b : pin_ring_in) b.release();
   for (PinnedBuf &b : pin_ring_out) b.release();

@@ -96,6 +96,8 @@ struct Workspace {
   bool busy = false;
   const char *mark_busy(cudaStream_t st);
   DevBuf in_stage, out_stage, x, y, t0, t1, seeds, blocks, misc;
+  DevBuf fdr_tickets;               // k_fdr's chunk ticket counter (counts up across launches; never reset)
+  unsigned fdr_ticket_base = 0;
   PinnedBuf pin_in, pin_out, pin_misc;
   PinnedBuf pin_ring_in[3], pin_ring_out[3];   // staging slots of the pageable-host batch pipeline
   // side stream for small kernels that may overlap the tail of a large one (k_fdr's head kernel), fenced by events
