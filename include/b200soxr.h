@@ -190,6 +190,14 @@ B200SOXR_API size_t b200soxr_output_frames(double input_rate, double output_rate
 B200SOXR_API size_t b200soxr_plan_dump(double input_rate, double output_rate, unsigned long quality,
                                        unsigned long q_flags, char *buf, size_t buf_size);
 
+/* Which kernels serve a conversion, in one line -- e.g. "b200-cr32 | exact grid (resample, streams): k_fft_stage[dft
+ * N=4096 2/1 + vpoly0 fused] | resample_batch default: k_fdr[2560 -> 2352 points, variant 1]" -- so that a plan that
+ * falls to the direct-form kernels is visible (the role of SOXR_TRACE's engine line, soxr.c:381-397).  `dtype` is
+ * the I/O type (it decides the arithmetic type).  Needs a CUDA device (the plan is built and cached).  Returns the
+ * bytes needed. */
+B200SOXR_API size_t b200soxr_describe_path(double input_rate, double output_rate, unsigned long quality, int dtype,
+                                           char *buf, size_t buf_size);
+
 /* Pure-host emulation of the reference's pull scheduler (cr.c:498-581): number of
  * output frames each soxr_process call of the given chunk partition returns.
  * chunk_lens[i] == 0 means a flush call (in == NULL).  Works without a GPU. */

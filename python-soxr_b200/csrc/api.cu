@@ -16,6 +16,7 @@
 #include <memory>
 #include <mutex>
 #include <new>
+#include <string>
 #include <vector>
 
 #include "../../include/b200soxr.h"
@@ -420,6 +421,26 @@ double b200soxr_delay(b200soxr_t p) {
 }
 size_t *b200soxr_num_clips(b200soxr_t p) { return &p->clips; }
 char const *b200soxr_engine(b200soxr_t p) { return p->dp->is_double ? "b200-cr64" : "b200-cr32"; }
+
+size_t b200soxr_describe_path(double input_rate, double output_rate, unsigned long quality, int dtype,
+                              char *buf, size_t buf_size) {
+  std::string text;
+  if (!(input_rate > 0) || !(output_rate > 0)) text = "error: I/O ratio out-of-range";
+  else if (dtype < 0 || dtype > 3) text = "error: invalid io datatype(s)";
+  else if (!device_ok()) text = std::string("error: ") + kNoDevice;
+  else {
+    const QSpec q = quality_spec(quality, 0);
+    std::shared_ptr<DevicePlan> dp;
+    const char *e = get_device_plan(input_rate / output_rate, q, RSpec(), 1.0, arith_double_for(q, dtype, dtype), &dp);
+    text = e ? std::string("error: ") + e : dp->path;
+  }
+  if (buf && buf_size) {
+    const size_t n = std::min(buf_size - 1, text.size());
+    std::memcpy(buf, text.data(), n);
+    buf[n] = 0;
+  }
+  return text.size() + 1;
+}
 
 b200soxr_error_t b200soxr_clear(b200soxr_t p) {
   if (!p) return "invalid soxr_t pointer";

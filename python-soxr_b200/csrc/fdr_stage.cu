@@ -413,6 +413,13 @@ const char *fdr_prepare(DevicePlan *dp) {
   if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg1_6>(dp, 12)) return e;
   if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg4_1>(dp, 13)) return e;
   if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg1_4>(dp, 14)) return e;
+  if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg441_320>(dp, 15)) return e;
+  if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg320_441>(dp, 16)) return e;
+  if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg147_80>(dp, 17)) return e;
+  if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg80_147>(dp, 18)) return e;
+  if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg320_147>(dp, 19)) return e;
+  if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg147_320>(dp, 20)) return e;
+  if (!dp->fdr) if (const char *e = prepare_cfg<FdrCfg160_441>(dp, 21)) return e;
   return nullptr;
 }
 
@@ -541,6 +548,13 @@ static const char *launch_variant(const FdrInfo &fi, const FdrKParams &P, long l
     case 12: return launch_cfg<FdrCfg1_6>(fi, P, n_items, st, ws);
     case 13: return launch_cfg<FdrCfg4_1>(fi, P, n_items, st, ws);
     case 14: return launch_cfg<FdrCfg1_4>(fi, P, n_items, st, ws);
+    case 15: return launch_cfg<FdrCfg441_320>(fi, P, n_items, st, ws);
+    case 16: return launch_cfg<FdrCfg320_441>(fi, P, n_items, st, ws);
+    case 17: return launch_cfg<FdrCfg147_80>(fi, P, n_items, st, ws);
+    case 18: return launch_cfg<FdrCfg80_147>(fi, P, n_items, st, ws);
+    case 19: return launch_cfg<FdrCfg320_147>(fi, P, n_items, st, ws);
+    case 20: return launch_cfg<FdrCfg147_320>(fi, P, n_items, st, ws);
+    case 21: return launch_cfg<FdrCfg160_441>(fi, P, n_items, st, ws);
   }
   return "internal: unknown fdr variant";
 }

@@ -18,7 +18,8 @@
 // steps of mr input / lr output samples on each side) that covers the composite filter's
 // half-width; the first outputs of a clip, where the reference's intermediate signal does not
 // exist before index 0 (cr.c:487-490), come from the head kernels (fdr_stage.cu).  One FdrCfg per
-// ratio family (160:147, 147:160, 2:1, 1:2, 3:1, 1:3, 3:2, 2:3, 441:160, 6:1, 1:6, 4:1, 1:4).
+// ratio family (160:147, 147:160, 2:1, 1:2, 3:1, 1:3, 3:2, 2:3, 441:160, 160:441, 6:1, 1:6, 4:1, 1:4, 441:320, 320:441,
+// 147:80, 80:147, 320:147, 147:320).
 //
 // FFTs: N = RA*RB*RC, three register-radix passes (decimation in time forward, the mirrored
 // decimation in frequency backward) with shared-memory exchanges whose strides are chosen so
@@ -274,6 +275,7 @@ typedef Fft3<8, 16, 10, 162, 136, kP2JFast> Fft1280;
 typedef Fft3<8, 10, 8, 82, 88, kP2JFast> Fft640;
 typedef Fft3<16, 15, 16, 240, 241, kP2Row16> Fft3840;   // all three passes have 240 tasks
 typedef Fft3<12, 21, 14, 294, 253, kP2Row16> Fft3528;
+typedef Fft3<12, 14, 7, 98, 169, kP2Row16> Fft1176;     // 98 / 84 / 168 tasks
 // 48000 -> 44100 family (io ratio 160/147): 2560 -> 2352 points, one grid step (160 in / 147 out) of margin per side
 typedef FdrCfg<Fft2560, Fft2352, 160, 147, 2, B2_FDR_THREADS, B2_FDR_MIN_CTAS> FdrCfg160_147;
 // 44100 -> 48000 family (147/160): the same two transforms with their roles swapped
@@ -299,6 +301,18 @@ typedef FdrCfg<Fft2560, Fft640, 4, 1, 224, 192, 4> FdrCfg4_1;
 typedef FdrCfg<Fft640, Fft2560, 1, 4, 208, 192, 4> FdrCfg1_4;
 // 44100 -> 16000 (441/160): 3528 -> 1280 points, one grid step (441 in / 160 out) of margin per side
 typedef FdrCfg<Fft3528, Fft1280, 441, 160, 2, 320, 3> FdrCfg441_160;   // 294 first-pass tasks in one round: 63 registers, no spills
+
+// 44100 <-> 32000 (441/320): 3528 <-> 2560 points, one grid step of margin per side
+typedef FdrCfg<Fft3528, Fft2560, 441, 320, 2, 320, 3> FdrCfg441_320;
+typedef FdrCfg<Fft2560, Fft3528, 320, 441, 2, 320, 3> FdrCfg320_441;
+// 88200 -> 48000, 44100 -> 24000 (147/80) and back: 2352 <-> 1280 points
+typedef FdrCfg<Fft2352, Fft1280, 147, 80, 4, 224, 4> FdrCfg147_80;
+typedef FdrCfg<Fft1280, Fft2352, 80, 147, 4, 192, 4> FdrCfg80_147;
+// 96000 -> 44100, 48000 -> 22050 (320/147) and back: 2560 <-> 1176 points
+typedef FdrCfg<Fft2560, Fft1176, 320, 147, 2, 192, 5> FdrCfg320_147;
+typedef FdrCfg<Fft1176, Fft2560, 147, 320, 2, 192, 5> FdrCfg147_320;
+// 16000 -> 44100 (160/441): 1280 -> 3528 points
+typedef FdrCfg<Fft1280, Fft3528, 160, 441, 2, 320, 3> FdrCfg160_441;
 
 struct FdrInfo {
   int variant = 0;          // 1: FdrCfg160_147, 2: FdrCfg147_160, 3: FdrCfg2_1, 4: FdrCfg1_2, 5: FdrCfg2_1w, 6: FdrCfg3_1, 7: FdrCfg1_3, 8: FdrCfg441_160, 9: FdrCfg3_2, 10: FdrCfg2_3, 11: FdrCfg6_1, 12: FdrCfg1_6, 13: FdrCfg4_1, 14: FdrCfg1_4

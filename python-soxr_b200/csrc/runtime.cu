@@ -5,6 +5,8 @@
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <cstdio>
+#include <cstdio>
 #include <map>
 #include <thread>
 
@@ -263,6 +265,37 @@ const char *get_device_plan(double io_ratio, const QSpec &q, const RSpec &r, dou
   }
   if (const char *e = fft_stage_prepare(dp.get())) return e;
   if (const char *e = fdr_prepare(dp.get())) return e;
+  {
+    // one line saying which kernels serve the plan (no silent fall-through to the slow paths)
+    std::string exact;
+    const size_t S = dp->plan.stages.size();
+    for (size_t i = 0; i < S; ++i) {
+      const Stage &st = dp->plan.stages[i];
+      const bool fused = dp->fft && dp->fft->stage_index == int(i);
+      char buf[128];
+      const char *kind = st.kind == kHalf ? "half-band" : st.kind == kDft ? "dft" : st.kind == kPoly ? "vpoly0"
+                       : st.kind == kPolyInterp ? "vpoly-interp" : "cubic";
+      if (fused) {
+        std::snprintf(buf, sizeof buf, "k_fft_stage[dft N=%d %d/%d%s]", st.dft_length, st.L, st.M,
+                      dp->fft->fused_poly ? " + vpoly0 fused" : "");
+        if (dp->fft->fused_poly) ++i;
+      } else {
+        std::snprintf(buf, sizeof buf, "%s[%s %d/%d direct form]",
+                      st.kind == kPolyInterp ? "k_poly_interp" : st.kind == kCubic ? "k_cubic" : "k_rational", kind, st.L, st.M);
+      }
+      exact += (exact.empty() ? "" : " -> ");
+      exact += buf;
+    }
+    if (exact.empty()) exact = "copy (unity ratio)";
+    std::string batch = "same as exact grid";
+    if (dp->fdr) {
+      char buf[96];
+      std::snprintf(buf, sizeof buf, "k_fdr[%d -> %d points, variant %d]", dp->fdr->nin, dp->fdr->nout, dp->fdr->variant);
+      batch = buf;
+    }
+    dp->path = std::string(dp->is_double ? "b200-cr64" : "b200-cr32") + " | exact grid (resample, streams): " + exact +
+               " | resample_batch default: " + batch;
+  }
   if (g_plans.size() >= kMaxCachedPlans) {
     auto victim = g_plans.begin();
     for (auto j = g_plans.begin(); j != g_plans.end(); ++j)

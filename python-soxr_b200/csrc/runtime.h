@@ -71,6 +71,8 @@ struct DevicePlan {
   std::vector<DevStage> stages;
   std::shared_ptr<FftStageInfo> fft;   // non-null if the fused FFT kernel applies
   std::shared_ptr<FdrInfo> fdr;        // non-null if the single-pass frequency-domain kernel applies (batches)
+  // which kernels this plan runs through: "b200-cr32 | exact: ... | batch: ..." (b200soxr_engine / b200soxr_describe_path)
+  std::string path;
   ~DevicePlan();
 };
 

@@ -113,6 +113,8 @@ def _load():
     L.b200soxr_quantize.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_size_t, C.POINTER(C.c_size_t), C.c_size_t,
                                     C.c_int, C.c_int, C.c_int, C.POINTER(C.c_ulonglong), C.c_void_p,
                                     C.POINTER(C.c_size_t)]
+    L.b200soxr_describe_path.restype = C.c_size_t
+    L.b200soxr_describe_path.argtypes = [C.c_double, C.c_double, C.c_ulong, C.c_int, C.c_char_p, C.c_size_t]
     L.b200soxr_launch_count.restype = C.c_ulonglong
     L.b200soxr_device_available.restype = C.c_int
     return L
@@ -147,6 +149,15 @@ def plan_dump(in_rate, out_rate, quality, q_flags=0):
     buf = C.create_string_buffer(n)
     _lib.b200soxr_plan_dump(in_rate, out_rate, quality, q_flags, buf, n)
     return buf.value.decode().splitlines()
+
+
+def describe_path(in_rate, out_rate, quality, dtype='float32'):
+    """One line naming the kernels that serve this conversion (exact grid and resample_batch default)."""
+    code = _DT_CODE[np.dtype(dtype)]
+    n = _lib.b200soxr_describe_path(in_rate, out_rate, int(quality), code, None, 0)
+    buf = C.create_string_buffer(n)
+    _lib.b200soxr_describe_path(in_rate, out_rate, int(quality), code, buf, n)
+    return buf.value.decode()
 
 
 def emulate_calls(in_rate, out_rate, quality, chunk_lens, olen_each=1 << 40, q_flags=0):

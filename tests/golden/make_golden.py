@@ -66,6 +66,14 @@ VECTOR_CASES = {
     'fam_f32_16k_48k_VHQ_mono':     (45, (5000,), 'float32', 16000, 48000, 'VHQ', 1.0),
     'fam_f32_44k1_16k_VHQ_3ch':     (46, (12000, 3), 'float32', 44100, 16000, 'VHQ', 1.0),
     'fam_i16_48k_16k_HQ_stereo':    (47, (9000, 2), 'int16', 48000, 16000, 'HQ', 5000.0),
+    # round-2 families: 441:320, 320:441, 147:80, 80:147, 320:147, 147:320, 160:441
+    'fam_f32_44k1_32k_VHQ_stereo':  (50, (14000, 2), 'float32', 44100, 32000, 'VHQ', 1.0),
+    'fam_f32_32k_44k1_HQ_stereo':   (51, (9000, 2), 'float32', 32000, 44100, 'HQ', 1.0),
+    'fam_f32_88k2_48k_HQ_stereo':   (52, (12000, 2), 'float32', 88200, 48000, 'HQ', 1.0),
+    'fam_f32_48k_88k2_HQ_mono':     (53, (6000,), 'float32', 48000, 88200, 'HQ', 1.0),
+    'fam_f32_96k_44k1_HQ_stereo':   (54, (12000, 2), 'float32', 96000, 44100, 'HQ', 1.0),
+    'fam_f32_22k05_48k_VHQ_3ch':    (55, (5000, 3), 'float32', 22050, 48000, 'VHQ', 1.0),
+    'fam_f32_16k_44k1_HQ_mono':     (56, (5000,), 'float32', 16000, 44100, 'HQ', 1.0),
 }
 
 STREAM_CASES = {

@@ -45,6 +45,20 @@ def test_float_matches_reference_golden_and_oracle(name):
     assert rms(y.astype(np.float64) - orc) <= tol
 
 
+@pytest.mark.parametrize("name", [n for n in sorted(META) if META[n]['dtype'] == 'float32'])
+def test_batch_kernel_matches_reference_golden(name):
+    # soxr.resample_batch: the single-pass frequency-domain kernel where the plan has a ratio family (the fam_*
+    # goldens, one per family), the exact-grid kernels otherwise -- against the unmodified reference's output
+    m = META[name]
+    x = case_input(m)
+    xb = np.stack([x, x[::-1].copy()])            # two clips: the golden one and its time reverse
+    y = soxr.resample_batch(xb, m['in_rate'], m['out_rate'], m['quality'])
+    ref = VEC[name]
+    assert y.dtype == np.float32 and y[0].shape == ref.shape
+    assert rms(y[0].astype(np.float64) - ref) <= TOL_F32
+    assert np.abs(y[0].astype(np.float64) - ref).max() <= 8e-6
+
+
 @pytest.mark.parametrize("name", [n for n in sorted(META) if META[n]['dtype'].startswith('int')])
 def test_int_matches_reference_after_rounding(name):
     m = META[name]
@@ -467,7 +481,9 @@ FDR_FAMILIES = [(44100, 48000, 'VHQ'), (96000, 48000, 'HQ'), (96000, 48000, 'VHQ
                 (22050, 44100, 'VHQ'), (44100, 22050, 'MQ'), (48000, 44100, 'HQ'), (48000, 16000, 'HQ'),
                 (48000, 16000, 'VHQ'), (16000, 48000, 'HQ'), (8000, 24000, 'VHQ'), (44100, 16000, 'HQ'),
                 (44100, 16000, 'VHQ'), (48000, 32000, 'HQ'), (32000, 48000, 'VHQ'),
-                (48000, 8000, 'HQ'), (48000, 8000, 'VHQ'), (8000, 48000, 'HQ'), (48000, 12000, 'HQ'), (12000, 48000, 'HQ')]
+                (48000, 8000, 'HQ'), (48000, 8000, 'VHQ'), (8000, 48000, 'HQ'), (48000, 12000, 'HQ'), (12000, 48000, 'HQ'),
+                (44100, 32000, 'HQ'), (44100, 32000, 'VHQ'), (32000, 44100, 'HQ'), (88200, 48000, 'HQ'), (44100, 24000, 'VHQ'),
+                (48000, 88200, 'HQ'), (96000, 44100, 'HQ'), (48000, 22050, 'VHQ'), (44100, 96000, 'HQ'), (16000, 44100, 'HQ')]
 
 
 @pytest.mark.parametrize("in_rate,out_rate,quality", FDR_FAMILIES)
@@ -517,3 +533,13 @@ def test_fdr_many_blocks_per_cta_is_batch_invariant(in_rate, out_rate, quality, 
     q = {'HQ': O.HQ, 'VHQ': O.VHQ}[quality]
     want = O.resample_f64(x[n_clips - 1], in_rate, out_rate, q)
     assert rms(y[n_clips - 1].astype(np.float64) - want) <= TOL_F32
+
+
+def test_describe_path_names_the_kernels():
+    # no silent fall-through: which kernels serve a plan is one call away
+    d = soxr_ext.describe_path(48000, 44100, soxr.VHQ, 'float32')
+    assert 'k_fft_stage' in d and 'vpoly0 fused' in d and 'k_fdr[2560 -> 2352' in d
+    assert 'b200-cr64' in soxr_ext.describe_path(48000, 44100, soxr.VHQ, 'float64')
+    assert 'k_fdr[3528 -> 2560' in soxr_ext.describe_path(44100, 32000, soxr.HQ, 'float32')
+    assert 'k_poly_interp' in soxr_ext.describe_path(44100, 47999.5, soxr.VHQ, 'float32')
+    assert 'same as exact grid' in soxr_ext.describe_path(44100, 47999.5, soxr.VHQ, 'float32')
