@@ -14,13 +14,22 @@
 
 namespace b2 {
 
+// element(s, k) = p[(s / channels) * clip_stride + (s % channels) * chan_stride + (k - base) * frame_stride]; planar
+// scratch is channels == 1, clip_stride == row stride, frame_stride == 1.  k_rational needs the planar form
+// (`stride`); k_poly_interp and k_cubic take any layout of engine-precision samples, so the first / last stage of a
+// plan reads / writes the caller's float buffers directly (no K1 / K7 copy pass).
 template <typename T>
 struct SigIn {
   const T *p;
-  size_t stride;
+  size_t stride;                                  // == clip_stride (planar form)
   long base, vlo, vhi;
+  long long chan_stride = 0, frame_stride = 1;
+  unsigned channels = 1;
+  __device__ __forceinline__ const T *sig(unsigned s) const {   // pointer to logical sample 0 of signal s
+    return p + (long long)(s / channels) * (long long)stride + (long long)(s % channels) * chan_stride - (long long)base * frame_stride;
+  }
   __device__ __forceinline__ T at(unsigned s, long k) const {
-    return (k >= vlo && k < vhi) ? p[size_t(s) * stride + size_t(k - base)] : T(0);
+    return (k >= vlo && k < vhi) ? sig(s)[(long long)k * frame_stride] : T(0);
   }
 };
 template <typename T>
@@ -28,7 +37,12 @@ struct SigOut {
   T *p;
   size_t stride;
   long base;
-  __device__ __forceinline__ T &at(unsigned s, long n) const { return p[size_t(s) * stride + size_t(n - base)]; }
+  long long chan_stride = 0, frame_stride = 1;
+  unsigned channels = 1;
+  __device__ __forceinline__ T *sig(unsigned s) const {
+    return p + (long long)(s / channels) * (long long)stride + (long long)(s % channels) * chan_stride - (long long)base * frame_stride;
+  }
+  __device__ __forceinline__ T &at(unsigned s, long n) const { return sig(s)[(long long)n * frame_stride]; }
 };
 
 // ---- K1: deinterleave + convert-in (role of data-io.c:13-57: plain C cast, no scaling)
@@ -127,10 +141,17 @@ __global__ void k_poly_interp(SigIn<T> in, const T *__restrict__ table, int n_ta
     for (int o = 1; o <= order; ++o) v = v * x + cj[o];   // Horner in engine precision, as the reference
     vs[j * blockDim.x] = v;
   }
+  const bool inside = pos >= in.vlo && pos + n_taps <= in.vhi;   // the whole window is real input: no per-tap checks
   const unsigned s_end = min(n_sig, (blockIdx.y + 1u) * spb);
   for (unsigned s = blockIdx.y * spb; s < s_end; ++s) {
     double acc = 0;
-    for (int j = 0; j < n_taps; ++j) acc = fma(double(vs[j * blockDim.x]), double(in.at(s, pos + j)), acc);
+    if (inside) {
+      const T *__restrict__ src = in.sig(s) + (long long)pos * in.frame_stride;
+      const long long fs = in.frame_stride;
+      for (int j = 0; j < n_taps; ++j) acc = fma(double(vs[j * blockDim.x]), double(src[j * fs]), acc);
+    } else {
+      for (int j = 0; j < n_taps; ++j) acc = fma(double(vs[j * blockDim.x]), double(in.at(s, pos + j)), acc);
+    }
     out.at(s, n) = T(acc);
   }
 }
@@ -148,7 +169,7 @@ __global__ void k_cubic(SigIn<T> in, unsigned long long step, double mult, SigOu
   const long p = long(whole);
   const double x = double(frac) * (1. / 4294967296.);
   for (unsigned s = blockIdx.y; s < n_sig; s += gridDim.y) {
-    const double s0 = in.at(s, p), s1 = in.at(s, p + 1), s2 = in.at(s, p + 2), sm = in.at(s, p - 1);
+    const double s0 = in.at(s, p), s1 = in.at(s, p + 1), s2 = in.at(s, p + 2), sm = in.at(s, p - 1);   // (any layout)
     const double b = .5 * (s1 + sm) - s0, a = (1 / 6.) * (s2 - s1 + sm - s0 - 4 * b), c = s1 - s0 - a - b;
     out.at(s, n) = T(mult * (((a * x + b) * x + c) * x + s0));
   }

@@ -482,6 +482,19 @@ const char *sig_copy(const SigDesc &in, const SigDesc &out, long o0, long o1, un
 template <typename T> bool is_planar(const SigDesc &d) {
   return d.dtype == (sizeof(T) == 8 ? 1 : 0) && d.frame_stride == 1 && d.channels == 1;
 }
+// engine-precision samples in any layout: what k_poly_interp / k_cubic read and write directly
+template <typename T> bool is_engine_type(const SigDesc &d) { return d.dtype == (sizeof(T) == 8 ? 1 : 0); }
+inline bool takes_any_layout(const Stage &s) { return s.kind == kPolyInterp || s.kind == kCubic; }
+template <typename T> SigIn<T> sig_in_of(const SigDesc &d) {
+  SigIn<T> g{static_cast<const T *>(d.p), size_t(d.clip_stride), d.base, d.vlo, d.vhi};
+  g.chan_stride = d.chan_stride; g.frame_stride = d.frame_stride; g.channels = d.channels;
+  return g;
+}
+template <typename T> SigOut<T> sig_out_of(const SigDesc &d) {
+  SigOut<T> g{static_cast<T *>(d.p), size_t(d.clip_stride), d.base};
+  g.chan_stride = d.chan_stride; g.frame_stride = d.frame_stride; g.channels = d.channels;
+  return g;
+}
 
 template <typename T>
 const char *run_stage_generic(const DevicePlan &dp, size_t si, SigIn<T> in, SigOut<T> out, Range r,
@@ -562,7 +575,8 @@ const char *run_range_t(const DevicePlan &dp, const SigDesc &in0, long n_in_tota
     const bool is_last = i + 1 == launches.size();
     const size_t len = size_t(std::max(0L, ln.r.hi - ln.r.lo));
     // generic kernels read planar engine-precision input only (K1 as a separate pass)
-    if (!ln.fft && !is_planar<T>(cur)) {
+    const bool any_layout = !ln.fft && takes_any_layout(dp.plan.stages[ln.first]);
+    if (!ln.fft && !is_planar<T>(cur) && !(any_layout && is_engine_type<T>(cur))) {
       const long lo = std::max(xin.lo, cur.vlo), hi = std::max(lo, std::min(xin.hi, cur.vhi));
       const size_t stride = (size_t(hi - lo) + 63) & ~size_t(63);
       if (const char *e = ws->x.reserve(std::max<size_t>(1, stride * n_sig) * sizeof(T))) return e;
@@ -572,7 +586,7 @@ const char *run_range_t(const DevicePlan &dp, const SigDesc &in0, long n_in_tota
     }
     SigDesc dst;
     DevBuf *dst_buf = nullptr;
-    const bool direct = is_last && (ln.fft || is_planar<T>(out0));
+    const bool direct = is_last && (ln.fft || is_planar<T>(out0) || (any_layout && is_engine_type<T>(out0)));
     if (direct) dst = out0;
     else {
       dst_buf = (cur_buf == &ws->t0) ? &ws->t1 : &ws->t0;
@@ -584,8 +598,8 @@ const char *run_range_t(const DevicePlan &dp, const SigDesc &in0, long n_in_tota
     const char *e;
     if (ln.fft) e = fft_stage_run(dp, *dp.fft, cur, dst, ln.r.lo, ln.r.hi, n_sig, group, st);
     else {
-      SigIn<T> gi{static_cast<const T *>(cur.p), size_t(cur.clip_stride), cur.base, cur.vlo, cur.vhi};
-      SigOut<T> go{static_cast<T *>(dst.p), size_t(dst.clip_stride), dst.base};
+      const SigIn<T> gi = sig_in_of<T>(cur);
+      const SigOut<T> go = sig_out_of<T>(dst);
       e = run_stage_generic<T>(dp, ln.first, gi, go, ln.r, n_sig, st);
     }
     if (e) return e;
