@@ -306,13 +306,13 @@ def resample_oneshot(x, in_rate, out_rate, quality='HQ'):
     return oneshot(in_rate, out_rate, x, quality)
 
 
-def trace_plan(in_rate, out_rate, quality, dtype='float32'):
+def trace_plan(in_rate, out_rate, quality, dtype='float32', q_flags=0, env=None):
     """Run soxr_create under SOXR_TRACE=1 in a subprocess and return the
     stderr plan lines (formats: SURVEY.md Appendix D; cr.c:232-233,440-441,484-485)."""
     import subprocess, sys
     code = ("import sys; sys.path.insert(0, %r); import ref_soxr as r; "
-            "h = r._create(%r, %r, 1, r._dt(%r), r._dt(%r), %r); r.lib().soxr_delete(h)"
-            % (_HERE, float(in_rate), float(out_rate), str(dtype), str(dtype), quality))
-    env = dict(os.environ, SOXR_TRACE="2")
+            "h = r._create(%r, %r, 1, r._dt(%r), r._dt(%r), %r, 0, %r); r.lib().soxr_delete(h)"
+            % (_HERE, float(in_rate), float(out_rate), str(dtype), str(dtype), quality, int(q_flags)))
+    env = dict(os.environ, SOXR_TRACE="2", **(env or {}))
     p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
     return p.stderr.splitlines()

@@ -54,14 +54,36 @@ QSpec to_qspec(const b200soxr_quality_spec_t &q) {
   if (s.stopband_begin > 2) s.stopband_begin = 2 - s.stopband_begin / 100;
   return s;
 }
+// libsoxr's run-time overrides from the environment (soxr.c:340-363,426-433): a number inside its range replaces the
+// field, a flag value replaces its bit field.  Read at every create like the reference does.
+void runtime_num(const char *name, int lo, int hi, unsigned *field) {
+  if (const char *e = std::getenv(name)) {
+    const int i = std::atoi(e);
+    if (i >= lo && i <= hi) *field = unsigned(i);
+  }
+}
+void runtime_flag(const char *name, unsigned n_bits, unsigned n_shift, unsigned long *flags) {
+  if (const char *e = std::getenv(name)) {
+    const int i = std::atoi(e);
+    const unsigned long mask = (1ul << n_bits) - 1;
+    if (i >= 0 && i <= int(mask)) *flags = (*flags & ~(mask << n_shift)) | ((unsigned long)i << n_shift);
+  }
+}
 RSpec to_rspec(const b200soxr_runtime_spec_t *r) {
   RSpec s;
   if (r) {
     s.log2_min_dft_size = r->log2_min_dft_size;
     s.log2_large_dft_size = r->log2_large_dft_size;
     s.coef_size_kbytes = r->coef_size_kbytes;
-    s.flags = r->flags;
+    s.flags = r->flags & 0xff;      // (the bits above are this library's own extensions)
   }
+  runtime_num("SOXR_MIN_DFT_SIZE", 8, 15, &s.log2_min_dft_size);
+  runtime_num("SOXR_LARGE_DFT_SIZE", 8, 20, &s.log2_large_dft_size);
+  runtime_num("SOXR_COEFS_SIZE", 100, 800, &s.coef_size_kbytes);
+  runtime_flag("SOXR_COEF_INTERP", 2, 0, &s.flags);
+  runtime_flag("SOXR_NOSMALLINTOPT", 1, 3, &s.flags);
+  // (SOXR_NUM_THREADS and SOXR_STRICT_BUF steer the reference's OpenMP loop and its buffering check; neither has a
+  // counterpart here)
   return s;
 }
 const double kFullScale[] = {1, 1, 65536. * 32768, 32768};   // soxr.c:377
@@ -324,7 +346,7 @@ size_t b200soxr_plan_dump(double in_rate, double out_rate, unsigned long quality
                           char *buf, size_t buf_size) {
   Plan p;
   const QSpec q = quality_spec(quality, q_flags);
-  const char *err = make_plan(in_rate / out_rate, q, RSpec(), 1.0, &p);
+  const char *err = make_plan(in_rate / out_rate, q, to_rspec(nullptr), 1.0, &p);
   std::string text = err ? std::string("error: ") + err + "\n" : p.trace;
   if (buf && buf_size) {
     const size_t n = std::min(buf_size - 1, text.size());
@@ -339,7 +361,7 @@ b200soxr_error_t b200soxr_emulate_calls(double in_rate, double out_rate, unsigne
                                         size_t olen_each, size_t *odone_each, double *delay_each) {
   Plan p;
   const QSpec q = quality_spec(quality, q_flags);
-  if (const char *err = make_plan(in_rate / out_rate, q, RSpec(), 1.0, &p)) return err;
+  if (const char *err = make_plan(in_rate / out_rate, q, to_rspec(nullptr), 1.0, &p)) return err;
   CallEmu emu(p);
   for (size_t i = 0; i < n_chunks; ++i) {
     const size_t od = chunk_lens[i] ? emu.process(chunk_lens[i], olen_each) : emu.flush(olen_each);
@@ -431,7 +453,7 @@ size_t b200soxr_describe_path(double input_rate, double output_rate, unsigned lo
   else {
     const QSpec q = quality_spec(quality, 0);
     std::shared_ptr<DevicePlan> dp;
-    const char *e = get_device_plan(input_rate / output_rate, q, RSpec(), 1.0, arith_double_for(q, dtype, dtype), &dp);
+    const char *e = get_device_plan(input_rate / output_rate, q, to_rspec(nullptr), 1.0, arith_double_for(q, dtype, dtype), &dp);
     text = e ? std::string("error: ") + e : dp->path;
   }
   if (buf && buf_size) {
@@ -696,7 +718,7 @@ b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *d, void co
   const double io_ratio = d->in_rate / d->out_rate;
   const QSpec q = quality_spec(d->quality, (d->flags & B200SOXR_BATCH_DOUBLE) ? B200SOXR_DOUBLE_PRECISION : 0);
   std::shared_ptr<DevicePlan> dp;
-  if (const char *e = get_device_plan(io_ratio, q, RSpec(), 1.0, arith_double_for(q, d->dtype, d->dtype), &dp)) return e;
+  if (const char *e = get_device_plan(io_ratio, q, to_rspec(nullptr), 1.0, arith_double_for(q, d->dtype, d->dtype), &dp)) return e;
   const size_t total = output_frames(io_ratio, d->ilen);
   if (odone) *odone = total;
   if (clips) *clips = 0;

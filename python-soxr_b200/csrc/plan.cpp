@@ -35,8 +35,9 @@ constexpr unsigned long kResetOnClear = 1ul << 31;
 QSpec quality_spec(unsigned long recipe, unsigned long flags) {
   QSpec s;
   const unsigned q = unsigned(recipe & 0xf);
-  if (q > 7 || (recipe & 0x30) || (recipe & 0x40)) {
-    // python-soxr only ever passes QQ..VHQ with linear phase (src/soxr/__init__.py:29-35)
+  if (q > 7 || (recipe & 0x30)) {
+    // python-soxr only ever passes QQ..VHQ with linear phase (src/soxr/__init__.py:29-35); the libsamplerate-style
+    // recipes (8..10) and the non-linear phase responses (lsx_fir_to_phase, filter.c:154-245) are not provided
     s.error = (q > 11) ? "invalid quality type" : "quality recipe not supported by b200soxr";
     return s;
   }
@@ -47,6 +48,7 @@ QSpec quality_spec(unsigned long recipe, unsigned long flags) {
   const double rej = s.precision * to_db(2.);
   s.passband_end = q == 1 ? 1385 / 2048. : 1 - .05 / to_3db(rej);
   if (q <= 2) s.flags = (s.flags & ~kRolloffNone) | kRolloffMedium;
+  if (recipe & 0x40) s.passband_end = 1 - .01 / to_3db(rej);   // SOXR_STEEP_FILTER (soxr.c:142-143)
   return s;
 }
 

@@ -217,7 +217,8 @@ class CSoxr:
     (b200soxr_create_batch; arrays are then [stream, frame, channel]); `low_latency` returns every output whose
     filter support has arrived instead of the reference's FFT-block bursts (B200SOXR_RT_LOW_LATENCY)."""
 
-    def __init__(self, in_rate, out_rate, num_channels, ntype, quality, vr=False, n_streams=1, low_latency=False):
+    def __init__(self, in_rate, out_rate, num_channels, ntype, quality, vr=False, n_streams=1, low_latency=False,
+                 q_flags=0):
         self.in_rate = float(in_rate)
         self.out_rate = float(out_rate)
         self.ntype = int(ntype)
@@ -229,7 +230,8 @@ class CSoxr:
         self._dtype = np.dtype(_DT_NAME[self.ntype])
         self._fsz = self._dtype.itemsize * self.channels
         io = _lib.b200soxr_io_spec(self.ntype, self.ntype)
-        qs = _lib.b200soxr_quality_spec(int(quality), 32 if vr else 0)
+        # `quality` is a libsoxr recipe (QQ..VHQ, optionally | 0x40 SOXR_STEEP_FILTER), q_flags its flags (roll-off ...)
+        qs = _lib.b200soxr_quality_spec(int(quality), (32 if vr else 0) | int(q_flags))
         rt = _lib.b200soxr_runtime_spec(1)
         if low_latency:
             rt.flags |= RT_LOW_LATENCY

@@ -172,3 +172,31 @@ def test_other_plans_full_second_vs_live_reference(in_rate, out_rate, quality, d
         assert (d == 0).mean() >= 0.999
     else:
         assert rms(y.astype(np.float64) - ref) <= 1e-6
+
+
+@pytest.mark.parametrize("in_rate,out_rate,recipe,q_flags,dtype", [
+    (48000, 44100, 4 | 0x40, 0, 'float32'),      # SOXR_STEEP_FILTER
+    (44100, 48000, 6 | 0x40, 0, 'float64'),
+    (44100, 48000, 6, 2, 'float32'),             # SOXR_ROLLOFF_NONE
+    (96000, 48000, 4, 1, 'float32'),             # SOXR_ROLLOFF_MEDIUM
+    (48000, 44100, 5, 0, 'float32'),             # 24-bit recipe
+    (44100, 32000, 7, 0, 'float64'),             # 32-bit recipe
+    (48000, 16000, 3, 0, 'int16')])              # 16-bit recipe (SOXR_16_BITQ)
+def test_non_default_quality_specs_vs_live_reference(in_rate, out_rate, recipe, q_flags, dtype):
+    # libsoxr recipes / flags python-soxr itself never passes, through the stream handle
+    _need_ref()
+    n = 30000
+    rng = np.random.default_rng(recipe * 7 + q_flags)
+    x = (np.round(rng.standard_normal((n, 2)) * 5000).astype(dtype) if dtype == 'int16'
+         else rng.standard_normal((n, 2)).astype(dtype))
+    code = {'float32': 0, 'float64': 1, 'int32': 2, 'int16': 3}[dtype]
+    a = soxr_ext.CSoxr(in_rate, out_rate, 2, code, recipe, q_flags=q_flags)
+    b = R.RefStream(in_rate, out_rate, 2, dtype=dtype, quality=recipe, q_flags=q_flags)
+    ya = getattr(a, 'process_' + dtype)(x, True)
+    yb = b.resample_chunk(x, last=True)
+    assert ya.shape == yb.shape and ya.dtype == yb.dtype
+    if dtype == 'int16':
+        assert np.abs(ya.astype(np.int64) - yb).max() <= 2
+    else:
+        tol = 1e-11 if (dtype == 'float64' and (recipe & 0xf) > 4) else 1e-6
+        assert rms(ya.astype(np.float64) - yb) <= tol

@@ -161,3 +161,32 @@ def test_planner_matches_live_reference_trace_on_random_rates(seed):
     quality = ['LQ', 'MQ', 'HQ', 'VHQ'][seed % 4]
     want = [l for l in R.trace_plan(in_rate, out_rate, quality) if l.startswith('fir_len') or '>>' in l]
     assert soxr_ext.plan_dump(in_rate, out_rate, Q[quality]) == want, (in_rate, out_rate, quality)
+
+
+# ---- non-default quality specs and libsoxr's run-time environment overrides (soxr.c:426-433) ----
+STEEP = 0x40                      # SOXR_STEEP_FILTER (soxr.h:299)
+ROLLOFF_MEDIUM, ROLLOFF_NONE = 1, 2
+
+
+@pytest.mark.skipif(not _ref_available(), reason="oracle/_ref/libsoxr_ref.so not built")
+@pytest.mark.parametrize("in_rate,out_rate,recipe,q_flags", [
+    (48000, 44100, 4 | STEEP, 0), (44100, 48000, 6 | STEEP, 0), (96000, 48000, 4 | STEEP, 0), (44100, 47999.5, 6 | STEEP, 0),
+    (48000, 44100, 4, ROLLOFF_MEDIUM), (48000, 44100, 6, ROLLOFF_NONE), (44100, 16000, 4, ROLLOFF_NONE),
+    (48000, 8000, 5, 0), (8000, 48000, 7, 0), (44100, 48000, 3, 0)])
+def test_planner_follows_non_default_quality_specs(in_rate, out_rate, recipe, q_flags):
+    import ref_soxr as R
+    want = [l for l in R.trace_plan(in_rate, out_rate, recipe, q_flags=q_flags) if l.startswith('fir_len') or '>>' in l]
+    assert soxr_ext.plan_dump(in_rate, out_rate, recipe, q_flags) == want
+
+
+@pytest.mark.skipif(not _ref_available(), reason="oracle/_ref/libsoxr_ref.so not built")
+@pytest.mark.parametrize("env", [{"SOXR_MIN_DFT_SIZE": "12"}, {"SOXR_LARGE_DFT_SIZE": "9", "SOXR_MIN_DFT_SIZE": "8"},
+                                 {"SOXR_COEFS_SIZE": "100"}, {"SOXR_COEF_INTERP": "2"}, {"SOXR_NOSMALLINTOPT": "1"},
+                                 {"SOXR_MIN_DFT_SIZE": "99"}])
+@pytest.mark.parametrize("in_rate,out_rate,quality", [(48000, 44100, 'HQ'), (44100, 47999.5, 'VHQ'), (8000, 48000, 'HQ')])
+def test_planner_reads_libsoxr_environment_overrides(env, in_rate, out_rate, quality, monkeypatch):
+    import ref_soxr as R
+    want = [l for l in R.trace_plan(in_rate, out_rate, quality, env=env) if l.startswith('fir_len') or '>>' in l]
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    assert soxr_ext.plan_dump(in_rate, out_rate, Q[quality]) == want, (env, in_rate, out_rate, quality)
