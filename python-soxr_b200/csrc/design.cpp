@@ -141,4 +141,129 @@ double inv_f_resp(double drop, double a) {
   return drop > .5 ? x : 1 - x;
 }
 
+// ---------------------------------------------------------------------------
+// fir_to_phase (filter.c:154-245)
+// ---------------------------------------------------------------------------
+namespace {
+// in-place radix-2 complex FFT, sign = -1 forward (e^{-i...}), +1 backward (unnormalised)
+void cfft(std::vector<double> &re, std::vector<double> &im, int sign) {
+  const size_t n = re.size();
+  for (size_t i = 1, j = 0; i < n; ++i) {
+    size_t bit = n >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) { std::swap(re[i], re[j]); std::swap(im[i], im[j]); }
+  }
+  const double pi = 3.14159265358979323846264338327950288;
+  for (size_t len = 2; len <= n; len <<= 1) {
+    const double ang = sign * 2 * pi / double(len);
+    for (size_t i = 0; i < n; i += len)
+      for (size_t k = 0; k < len / 2; ++k) {
+        const double c = std::cos(ang * double(k)), s = std::sin(ang * double(k));
+        const size_t a = i + k, b = a + len / 2;
+        const double tr = re[b] * c - im[b] * s, ti = re[b] * s + im[b] * c;
+        re[b] = re[a] - tr; im[b] = im[a] - ti;
+        re[a] += tr; im[a] += ti;
+      }
+  }
+}
+// The reference's real transform pair in its own (Ooura) convention on the unpacked array
+//   w[2k] = R_k = sum_j a_j cos(2 pi j k / n),  w[2k+1] = I_k = sum_j a_j sin(2 pi j k / n),  k = 0 .. n/2
+// (I_k is MINUS the imaginary part of the usual DFT); the backward transform followed by the 2/n scaling of
+// filter.c:190,215 is the exact inverse.
+void real_forward(std::vector<double> &w, int n) {       // w: n reals in, n + 2 values (R, I pairs) out
+  std::vector<double> re(w.begin(), w.begin() + n), im(size_t(n), 0.);
+  cfft(re, im, -1);
+  for (int k = 0; k <= n / 2; ++k) { w[size_t(2 * k)] = re[size_t(k)]; w[size_t(2 * k + 1)] = -im[size_t(k)]; }
+}
+void real_backward_scaled(std::vector<double> &w, int n) {   // n + 2 values (R, I pairs) in, n reals out
+  std::vector<double> re(size_t(n), 0.), im(size_t(n), 0.);
+  for (int k = 0; k <= n / 2; ++k) {
+    re[size_t(k)] = w[size_t(2 * k)];
+    im[size_t(k)] = (k == 0 || k == n / 2) ? 0. : -w[size_t(2 * k + 1)];
+    if (k && k < n / 2) { re[size_t(n - k)] = re[size_t(k)]; im[size_t(n - k)] = -im[size_t(k)]; }
+  }
+  cfft(re, im, +1);
+  for (int j = 0; j < n; ++j) w[size_t(j)] = re[size_t(j)] / double(n);
+}
+double safe_log(double x) { return x != 0 ? std::log(x) : -26; }
+}  // namespace
+
+void fir_to_phase(std::vector<double> *h, int *post_len, double phase) {
+  const double pi = 3.14159265358979323846264338327950288;
+  const double phase1 = (phase > 50 ? 100 - phase : phase) / 50;
+  int len = int(h->size());
+  int work_len = 2 * 2 * 8;
+  for (int i = len; i > 1; work_len <<= 1, i >>= 1) {}
+  std::vector<double> work(size_t(work_len) + 2, 0.), pi_wraps(size_t(work_len) / 2 + 1, 0.);
+  for (int i = 0; i < len; ++i) work[size_t(i)] = (*h)[size_t(i)];
+  real_forward(work, work_len);                                   // cepstral
+  double prev_angle2 = 0, cum_2pi = 0, prev_angle1 = 0, cum_1pi = 0;
+  for (int i = 0; i <= work_len; i += 2) {
+    double angle = std::atan2(work[size_t(i) + 1], work[size_t(i)]);
+    double detect = 2 * pi;
+    double delta = angle - prev_angle2;
+    double adjust = detect * (double(delta < -detect * .7) - double(delta > detect * .7));
+    prev_angle2 = angle;
+    cum_2pi += adjust;
+    angle += cum_2pi;
+    detect = pi;
+    delta = angle - prev_angle1;
+    adjust = detect * (double(delta < -detect * .7) - double(delta > detect * .7));
+    prev_angle1 = angle;
+    cum_1pi += std::fabs(adjust);                                 // fabs for when 2pi and 1pi have combined
+    pi_wraps[size_t(i >> 1)] = cum_1pi;
+    work[size_t(i)] = safe_log(std::sqrt(work[size_t(i)] * work[size_t(i)] + work[size_t(i) + 1] * work[size_t(i) + 1]));
+    work[size_t(i) + 1] = 0;
+  }
+  real_backward_scaled(work, work_len);
+  for (int i = 1; i < work_len / 2; ++i) {                        // window to reject acausal components
+    work[size_t(i)] *= 2;
+    work[size_t(i + work_len / 2)] = 0;
+  }
+  work[size_t(work_len)] = work[size_t(work_len) + 1] = 0;
+  real_forward(work, work_len);
+  // the reference keeps R_{n/2} packed in slot 1 and leaves slots n, n+1 alone in this second half: mirror that
+  const double nyq_log = work[size_t(work_len)];
+  for (int i = 2; i < work_len; i += 2)                           // interpolate between linear & min phase
+    work[size_t(i) + 1] = phase1 * i / work_len * pi_wraps[size_t(work_len >> 1)] +
+                          (1 - phase1) * (work[size_t(i) + 1] + pi_wraps[size_t(i >> 1)]) - pi_wraps[size_t(i >> 1)];
+  work[0] = std::exp(work[0]);
+  const double nyq = std::exp(nyq_log);
+  for (int i = 2; i < work_len; i += 2) {
+    const double x = std::exp(work[size_t(i)]);
+    const double a = work[size_t(i) + 1];
+    work[size_t(i)] = x * std::cos(a);
+    work[size_t(i) + 1] = x * std::sin(a);
+  }
+  work[1] = 0;
+  work[size_t(work_len)] = nyq;
+  work[size_t(work_len) + 1] = 0;
+  real_backward_scaled(work, work_len);
+
+  int peak = 0, imp_peak = 0;
+  double imp_sum = 0, peak_imp_sum = 0;
+  for (int i = 0; i <= int(pi_wraps[size_t(work_len >> 1)] / pi + .5); ++i) {   // find peak pos.
+    imp_sum += work[size_t(i)];
+    if (std::fabs(imp_sum) > std::fabs(peak_imp_sum)) { peak_imp_sum = imp_sum; peak = i; }
+    if (work[size_t(i)] > work[size_t(imp_peak)]) imp_peak = i;
+  }
+  while (peak && std::fabs(work[size_t(peak - 1)]) > std::fabs(work[size_t(peak)]) && work[size_t(peak - 1)] * work[size_t(peak)] > 0) --peak;
+  int begin, end;
+  if (phase1 == 0) begin = 0;
+  else if (phase1 == 1) begin = peak - len / 2;
+  else {
+    begin = int((.997 - (2 - phase1) * .22) * len + .5);
+    end = int((.997 + (0 - phase1) * .22) * len + .5);
+    begin = peak - (begin & ~3);
+    end = peak + 1 + ((end + 3) & ~3);
+    len = end - begin;
+  }
+  std::vector<double> out(static_cast<size_t>(len));
+  for (int i = 0; i < len; ++i)
+    out[size_t(i)] = work[size_t((begin + (phase > 50 ? len - 1 - i : i) + work_len) & (work_len - 1))];
+  *post_len = phase > 50 ? peak - begin : begin + len - (peak + 1);
+  h->swap(out);
+}
+
 }  // namespace b2

@@ -23,6 +23,13 @@ struct LpfDesign {
 LpfDesign design_lpf(double fp, double fs, double fn, double att_db, int num_taps, int k,
                      double beta, bool dry_run);
 
+// Non-linear phase responses (quality recipes SOXR_MINIMUM_PHASE / INTERMEDIATE_PHASE / MAXIMUM_PHASE or an explicit
+// quality_spec.phase_response): turns the symmetric prototype `h` into the filter with the same magnitude response and
+// `phase` per cent of the way from minimum (0) over linear (50) to maximum (100) phase, by the cepstral method of
+// filter.c:154-245 (restated with a plain radix-2 complex FFT instead of Ooura's packed real FFT).  *post_len
+// receives the number of taps after the impulse peak (the stage's delay bookkeeping, cr.c:199-201).
+void fir_to_phase(std::vector<double> *h, int *post_len, double phase);
+
 double f_resp(double t, double a);                            // filter.c:253-268
 double inv_f_resp(double drop_db, double a);                  // filter.c:270-277
 inline double to_3db(double a) { return 1 - inv_f_resp(-3., a); }   // filter.h:42

@@ -40,12 +40,24 @@ enum { kP2JFast = 0, kP2Row16 = 1 };
 // ceil(log2 R) loads on the L1 data pipe + the rest on the FMA pipe replace R-1 loads: the L1 pipe is
 // the busier of the two in k_fdr (profiles/r1j: 68 % vs 40 %).
 __host__ __device__ constexpr int fdr_top_bit(int m) { return m >= 16 ? 16 : m >= 8 ? 8 : m >= 4 ? 4 : m >= 2 ? 2 : 1; }   // m < 32
+#ifndef B2_FDR_TW_SPARSE
+#define B2_FDR_TW_SPARSE 0
+#endif
 template <int R, typename C>
 __host__ __device__ __forceinline__ void twiddle_set(const C *__restrict__ tw, int stride, C (&w)[R]) {
   static_assert(R <= 32, "fdr_top_bit covers m < 32");
+#if B2_FDR_TW_SPARSE
+  // only w^1, w^4, w^16 come from the table; w^2 = w^1 * w^1 and w^8 = w^4 * w^4 are one product of table entries
+  // like every other member of the set (the L1 data pipe is the busiest unit of k_fdr: 75 %)
+#pragma unroll
+  for (int m = 1; m < R; m *= 4) w[m] = tw[m * stride];
+#pragma unroll
+  for (int m = 2; m < R; m *= 4) w[m] = cmul(w[m / 2], w[m / 2]);
+#else
 #pragma unroll
   for (int m = 1; m < R; ++m)
     if (fdr_top_bit(m) == m) w[m] = tw[m * stride];
+#endif
 #pragma unroll
   for (int m = 3; m < R; ++m)
     if (fdr_top_bit(m) != m) w[m] = cmul(w[fdr_top_bit(m)], w[m - fdr_top_bit(m)]);

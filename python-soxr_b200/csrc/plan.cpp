@@ -35,14 +35,15 @@ constexpr unsigned long kResetOnClear = 1ul << 31;
 QSpec quality_spec(unsigned long recipe, unsigned long flags) {
   QSpec s;
   const unsigned q = unsigned(recipe & 0xf);
-  if (q > 7 || (recipe & 0x30)) {
-    // python-soxr only ever passes QQ..VHQ with linear phase (src/soxr/__init__.py:29-35); the libsamplerate-style
-    // recipes (8..10) and the non-linear phase responses (lsx_fir_to_phase, filter.c:154-245) are not provided
+  if (q > 7) {
+    // python-soxr only ever passes QQ..VHQ (src/soxr/__init__.py:29-35); the libsamplerate-style recipes (8..10) and
+    // SOXR_PRECISIONQ are not provided
     s.error = (q > 11) ? "invalid quality type" : "quality recipe not supported by b200soxr";
     return s;
   }
   s.flags = flags | kResetOnClear;
-  s.phase_response = 50;
+  static const double kPhase[4] = {50, 25, 100, 0};   // "\\62\\31\\144"[(recipe & 0x30) >> 4], soxr.c:118 (index 3 is the NUL)
+  s.phase_response = kPhase[(recipe & 0x30) >> 4];
   s.stopband_begin = 1;
   s.precision = q == 0 ? 0 : q <= 3 ? 16 : 4 + q * 4;
   const double rej = s.precision * to_db(2.);
@@ -122,7 +123,7 @@ void tracef(std::string *t, const char *fmt, ...) {
 }
 
 // Overlap-save ("DFT") stage: L-fold zero-stuffing, Kaiser LPF, M-fold decimation.
-Stage make_dft_stage(double Fp, double Fs, double Fn, double att, int L, int M, double gain,
+Stage make_dft_stage(double Fp, double Fs, double Fn, double att, double phase_response, int L, int M, double gain,
                      const RSpec &r, std::string *trace) {
   Stage s;
   s.kind = kDft;
@@ -130,10 +131,14 @@ Stage make_dft_stage(double Fp, double Fs, double Fn, double att, int L, int M, 
   s.M = M;
   s.f_domain_m = std::abs(3 - M) == 1 && Fs <= 1;
   s.fd_shift = s.f_domain_m ? M / 2 : 0;
-  const int k = (is_pow2(L) && Fn == L) ? 2 * L : 4;     // tap-count granularity, cr.c:196
+  const int k = (phase_response == 50 && is_pow2(L) && Fn == L) ? 2 * L : 4;     // tap-count granularity, cr.c:196
   LpfDesign d = design_lpf(Fp, Fs, Fn, att, 0, -k, -1., false);
+  int post_peak = d.num_taps / 2;                         // linear phase, cr.c:201
+  if (phase_response != 50) {                             // cr.c:199-200
+    fir_to_phase(&d.h, &post_peak, phase_response);
+    d.num_taps = int(d.h.size());
+  }
   s.num_taps = d.num_taps;
-  const int post_peak = d.num_taps / 2;                   // linear phase, cr.c:201
   s.dft_length = pick_dft_length(d.num_taps, int(r.log2_min_dft_size), int(r.log2_large_dft_size));
   s.g = std::move(d.h);
   for (double &v : s.g) v *= L * gain;                    // cr.c:206 (FFT normalisation cancels)
@@ -187,7 +192,8 @@ const char *make_plan(double io_ratio, const QSpec &q, const RSpec &r, double mu
   const double Fp0 = q.passband_end, Fs0 = q.stopband_begin, tbw0 = Fs0 - Fp0;
   if (q.error) return q.error;
   if (q.flags & 32) return "variable-rate (SOXR_VR) is not supported by b200soxr";
-  if (q.phase_response != 50) return "only linear phase is supported by b200soxr";
+  const double phase_response = q.phase_response;
+  if (0 > phase_response || phase_response > 100) return "phase response not in [0, 100]";   // cr.c:308-309
   if (io_ratio < 1 && Fs0 - 1 > 1 - Fp0 / tol) return "imaging greater than rolloff";
   if (.002 / tol > tbw0 || tbw0 > .5 * tol) return "transition bandwidth not in [0.2,50] % of nyquist";
   if (.5 / tol > Fp0 || Fs0 > 1.5 * tol) return "transition band not within [50,150] % of nyquist";
@@ -211,7 +217,7 @@ const char *make_plan(double io_ratio, const QSpec &q, const RSpec &r, double mu
   const bool lq_bits = (q.flags & 64) ? bits <= 16 : bits == 16;
   const bool lq_Fp0 = (q.flags & 64) ? Fp0 <= lq_bw0 : Fp0 == lq_bw0;
   int mode = (lq_bits && rolloff == kRolloffMedium)
-                 ? int(io_ratio > 1 || !lq_Fp0 || Fs0 != 1)
+                 ? int(io_ratio > 1 || phase_response != 50 || !lq_Fp0 || Fs0 != 1)
                  : (int(std::ceil(bits1)) - 6) / 4;
   bool again = bits != 0;
   bool first_pass_flag = true;   // mirrors the reference's `n` (1 unless a re-plan was requested)
@@ -320,7 +326,7 @@ const char *make_plan(double io_ratio, const QSpec &q, const RSpec &r, double mu
   double Fp1 = Fp0, Fs1 = Fs0;
   if (have_pre) {
     const double Fn1 = preM ? std::max(preL, preM) : arbM / arbL;
-    P.stages.push_back(make_dft_stage(Fp1, Fs1, Fn1, att, preL, std::max(preM, 1), multiplier, r, &P.trace));
+    P.stages.push_back(make_dft_stage(Fp1, Fs1, Fn1, att, phase_response, preL, std::max(preM, 1), multiplier, r, &P.trace));
     multiplier = 1;
     Fp1 /= Fn1;
     Fs1 /= Fn1;
@@ -404,7 +410,7 @@ const char *make_plan(double io_ratio, const QSpec &q, const RSpec &r, double mu
   // ---- 5. post DFT stage (cr.c:478-482) -----------------------------------------
   if (have_post)
     P.stages.push_back(make_dft_stage(Fp0 / (upsample ? alpha : 1), upsample ? std::max(2 - Fs0 / alpha, 1.) : Fs0,
-                                      double(std::max(postL, postM)), att, postL, postM, multiplier, r, &P.trace));
+                                      double(std::max(postL, postM)), att, phase_response, postL, postM, multiplier, r, &P.trace));
 
   tracef(&P.trace, "%g: >>%i %i/%i %i/%g %i/%i (%x)", 1 / io_ratio, shr, preL, preM, arbL, arbM, postL,
          postM, P.is_double ? 0xf : 0xe);

@@ -178,7 +178,7 @@ const char *upload(const std::vector<double> &v, DevBuf *dst) {
 
 struct PlanKey {
   unsigned long long ratio_bits, gain_bits;
-  double precision, passband_end, stopband_begin;
+  double precision, passband_end, stopband_begin, phase_response;
   unsigned long qflags, rflags;
   unsigned min_dft, large_dft, coef_kb;
   int device, arith_double;
@@ -234,6 +234,7 @@ const char *get_device_plan(double io_ratio, const QSpec &q, const RSpec &r, dou
   key.precision = q.precision;
   key.passband_end = q.passband_end;
   key.stopband_begin = q.stopband_begin;
+  key.phase_response = q.phase_response;
   key.qflags = q.flags;
   key.rflags = r.flags & 0xff;
   key.min_dft = r.log2_min_dft_size;

@@ -15,7 +15,7 @@ for ir, orr, q, shape, dt in cases:
     x = rng.standard_normal(shape).astype(dt)
     t = time.time()
     try:
-        y = soxr.resample(x, ir, orr, q)
+        y = soxr.resample_batch(x[None], ir, orr, q)[0]
     except Exception as e:
         print(ir, orr, q, shape, dt, 'ERROR', e); continue
     dtm = time.time() - t

@@ -181,7 +181,13 @@ def test_other_plans_full_second_vs_live_reference(in_rate, out_rate, quality, d
     (96000, 48000, 4, 1, 'float32'),             # SOXR_ROLLOFF_MEDIUM
     (48000, 44100, 5, 0, 'float32'),             # 24-bit recipe
     (44100, 32000, 7, 0, 'float64'),             # 32-bit recipe
-    (48000, 16000, 3, 0, 'int16')])              # 16-bit recipe (SOXR_16_BITQ)
+    (48000, 16000, 3, 0, 'int16'),               # 16-bit recipe (SOXR_16_BITQ)
+    (48000, 44100, 4 | 0x10, 0, 'float32'),      # SOXR_INTERMEDIATE_PHASE (lsx_fir_to_phase, filter.c:154-245)
+    (48000, 44100, 4 | 0x30, 0, 'float32'),      # SOXR_MINIMUM_PHASE
+    (44100, 48000, 6 | 0x20, 0, 'float64'),      # SOXR_MAXIMUM_PHASE
+    (96000, 48000, 4 | 0x30, 0, 'float32'),      # minimum phase, single 1/2 DFT stage
+    (48000, 8000, 6 | 0x10, 0, 'float64'),       # half-band + DFT 1/3, intermediate phase
+    (44100, 47999.5, 4 | 0x30, 0, 'float32')])   # irrational ratio, minimum phase
 def test_non_default_quality_specs_vs_live_reference(in_rate, out_rate, recipe, q_flags, dtype):
     # libsoxr recipes / flags python-soxr itself never passes, through the stream handle
     _need_ref()
@@ -198,5 +204,11 @@ def test_non_default_quality_specs_vs_live_reference(in_rate, out_rate, recipe, 
     if dtype == 'int16':
         assert np.abs(ya.astype(np.int64) - yb).max() <= 2
     else:
-        tol = 1e-11 if (dtype == 'float64' and (recipe & 0xf) > 4) else 1e-6
+        tol = 1e-11 if (dtype == 'float64' and (recipe & 0xf) > 4 and not (recipe & 0x30)) else 1e-6
+        if dtype == 'float64' and (recipe & 0x30):
+            # lsx_fir_to_phase takes logs of the prototype's stop band (1e-9 at VHQ): the taps the reference ends up
+            # with carry 1e-6-level rounding noise of its own FFT (Ooura's rdft here, a plain radix-2 FFT in
+            # csrc/design.cpp), so two correct implementations of filter.c:154-245 agree to about 1e-5 at 28 bits
+            # and to 1e-9 at 20 bits (measured tap differences: 9.7e-7 / 5e-10 max)
+            tol = 2e-5 if (recipe & 0xf) > 4 else 1e-8
         assert rms(ya.astype(np.float64) - yb) <= tol

@@ -172,7 +172,10 @@ ROLLOFF_MEDIUM, ROLLOFF_NONE = 1, 2
 @pytest.mark.parametrize("in_rate,out_rate,recipe,q_flags", [
     (48000, 44100, 4 | STEEP, 0), (44100, 48000, 6 | STEEP, 0), (96000, 48000, 4 | STEEP, 0), (44100, 47999.5, 6 | STEEP, 0),
     (48000, 44100, 4, ROLLOFF_MEDIUM), (48000, 44100, 6, ROLLOFF_NONE), (44100, 16000, 4, ROLLOFF_NONE),
-    (48000, 8000, 5, 0), (8000, 48000, 7, 0), (44100, 48000, 3, 0)])
+    (48000, 8000, 5, 0), (8000, 48000, 7, 0), (44100, 48000, 3, 0),
+    # non-linear phase recipes: the tap counts after lsx_fir_to_phase are part of the trace
+    (48000, 44100, 4 | 0x10, 0), (48000, 44100, 4 | 0x30, 0), (44100, 48000, 6 | 0x20, 0), (96000, 48000, 4 | 0x30, 0),
+    (44100, 47999.5, 6 | 0x10, 0), (48000, 8000, 4 | 0x30, 0), (48000, 44100, 1 | 0x30, 0)])
 def test_planner_follows_non_default_quality_specs(in_rate, out_rate, recipe, q_flags):
     import ref_soxr as R
     want = [l for l in R.trace_plan(in_rate, out_rate, recipe, q_flags=q_flags) if l.startswith('fir_len') or '>>' in l]
