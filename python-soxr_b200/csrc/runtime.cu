@@ -124,7 +124,7 @@ class CopyPool {
   CopyPool() {
     unsigned n = std::thread::hardware_concurrency();
     if (const char *e = std::getenv("B200SOXR_COPY_THREADS")) n = unsigned(std::max(1L, std::atol(e)));
-    else n = std::max(1u, std::min(8u, n / 2));
+    else n = std::max(1u, std::min(16u, n));   // measured on a 16-vCPU B200 host: 2 / 4 / 8 / 16 threads -> 46.5 / 23.4 / 15.1 / 13.2 ms per 754 MB batch
     for (unsigned i = 1; i < n; ++i) workers_.emplace_back([this] { loop(); });
     for (std::thread &t : workers_) t.detach();
   }
