@@ -336,6 +336,17 @@ const char *launch_cfg_t(const FdrInfo &fi, FdrKParams P, long long n_items, cud
         cudaGetLastError();
         c.per_sm = 1;
       }
+      // Every resident CTA holds TM_COLS of the SM's 512 tensor-memory columns for its whole life.  The occupancy
+      // calculator answers 1 CTA per SM for any kernel that allocates tensor memory (measured: grid 148 instead of
+      // 740, profiles/r2q); the hardware co-schedules as many as registers, shared memory and columns allow, which
+      // is what __launch_bounds__(THREADS, MIN_CTAS) and the buffer sizes were chosen for.
+      if (Cfg::TM_OK && B2_FDR_TMEM != 0) {
+        cudaFuncAttributes fa;
+        size_t static_smem = 1056;
+        if (cudaFuncGetAttributes(&fa, kern) == cudaSuccess) static_smem = fa.sharedSizeBytes;
+        const int by_smem = int((228u << 10) / (smem_bytes + static_smem + 1024));   // 228 kB per SM, 1 kB reserved per CTA
+        c.per_sm = std::max(c.per_sm, std::min(std::min(Cfg::MIN_CTAS, by_smem), 512 / Cfg::TM_COLS));
+      }
       if (cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || c.sm_count < 1)
         c.sm_count = 148;
       c.set = true;

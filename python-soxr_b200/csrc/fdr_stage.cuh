@@ -43,6 +43,14 @@ __host__ __device__ constexpr int fdr_top_bit(int m) { return m >= 16 ? 16 : m >
 #ifndef B2_FDR_TW_SPARSE
 #define B2_FDR_TW_SPARSE 0
 #endif
+__host__ __device__ constexpr int fdr_np2(int R) { return R > 16 ? 5 : R > 8 ? 4 : R > 4 ? 3 : R > 2 ? 2 : 1; }   // powers of two in [1, R)
+// the members of the set that are not powers of two, from the ones that are
+template <int R, typename C>
+__host__ __device__ __forceinline__ void twiddle_products(C (&w)[R]) {
+#pragma unroll
+  for (int m = 3; m < R; ++m)
+    if (fdr_top_bit(m) != m) w[m] = cmul(w[fdr_top_bit(m)], w[m - fdr_top_bit(m)]);
+}
 template <int R, typename C>
 __host__ __device__ __forceinline__ void twiddle_set(const C *__restrict__ tw, int stride, C (&w)[R]) {
   static_assert(R <= 32, "fdr_top_bit covers m < 32");
@@ -146,6 +154,29 @@ struct Fft3 {
     for (int q = 0; q < RC; ++q) h[q] = H[t + T3 * q];
   }
 
+  // The same per-thread constants as 32-bit words (the form they are kept in tensor memory in, see tmem_* below):
+  // the NP2C power-of-two twiddles of the third pass, and the thread's RC response bins.
+  static constexpr int NP2C = fdr_np2(RC);
+  static __device__ __forceinline__ void tw3_words(int tau, const float2 *__restrict__ tw3, unsigned (&r)[2 * NP2C]) {
+    const int t = tau < T3 ? tau : T3 - 1;
+#pragma unroll
+    for (int i = 0; i < NP2C; ++i) {
+      const float2 v = tw3[t + T3 * (1 << i)];
+      r[2 * i] = __float_as_uint(v.x);
+      r[2 * i + 1] = __float_as_uint(v.y);
+    }
+  }
+  static __device__ __forceinline__ void tw3_from_words(const unsigned *r, float2 (&w)[RC]) {
+#pragma unroll
+    for (int i = 0; i < NP2C; ++i) w[1 << i] = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+    twiddle_products<RC>(w);
+  }
+  static __device__ __forceinline__ void h_words(int tau, const float *__restrict__ H, unsigned (&r)[RC]) {
+    const int t = tau < T3 ? tau : T3 - 1;
+#pragma unroll
+    for (int q = 0; q < RC; ++q) r[q] = __float_as_uint(H[t + T3 * q]);
+  }
+
   template <typename C>
   static __host__ __device__ __forceinline__ void fwd_p2(int tau, const C *__restrict__ E1, C *__restrict__ E2,
                                                          const C (&w)[RB]) {
@@ -235,6 +266,122 @@ struct Fft3 {
   }
 };
 
+
+#ifdef __CUDACC__
+// ---- tensor memory (TMEM) as a per-thread constant store ---------------------------------------
+// The per-thread constants of a block (the power-of-two twiddles of the two third passes and the
+// thread's RC filter-response bins) are the same for every block a CTA walks.  Registers cannot
+// hold them (64 per thread at 5 CTAs/SM), and re-reading them from L1 costs 18 % of the wavefronts
+// of the L1 data pipe, the busiest unit of k_fdr (profiles/r2o_ncu_summary.txt: 75 %).  Blackwell's
+// tensor memory (256 kB per SM, 128 lanes x 512 columns x 32 bit, read with tcgen05.ld over its own
+// datapath) holds them instead: lane = 32 (warp % 4) + lane id, 32-column slot (warp / 4), i.e.
+// a private array of 32 words per thread, written once per CTA (tcgen05.st) and read back per
+// block (tcgen05.ld.32x32b: one word per lane and column).  No tensor-core instruction is involved.
+#ifndef B2_FDR_TMEM
+#define B2_FDR_TMEM 1
+#endif
+__device__ __forceinline__ void tmem_alloc(unsigned *dst_smem, unsigned ncols) {   // one whole warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(unsigned taddr, unsigned ncols) {     // one whole warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+template <int N> struct TmemIo;
+template <> struct TmemIo<1> {
+  static __device__ __forceinline__ void ld(unsigned a, unsigned *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(a));
+  }
+  static __device__ __forceinline__ void st(unsigned a, const unsigned *r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(a), "r"(r[0]) : "memory");
+  }
+};
+template <> struct TmemIo<2> {
+  static __device__ __forceinline__ void ld(unsigned a, unsigned *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+  }
+  static __device__ __forceinline__ void st(unsigned a, const unsigned *r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(a), "r"(r[0]), "r"(r[1]) : "memory");
+  }
+};
+template <> struct TmemIo<4> {
+  static __device__ __forceinline__ void ld(unsigned a, unsigned *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(a));
+  }
+  static __device__ __forceinline__ void st(unsigned a, const unsigned *r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+                 "r"(r[3])
+                 : "memory");
+  }
+};
+template <> struct TmemIo<8> {
+  static __device__ __forceinline__ void ld(unsigned a, unsigned *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(a));
+  }
+  static __device__ __forceinline__ void st(unsigned a, const unsigned *r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(a), "r"(r[0]),
+                 "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+  }
+};
+template <> struct TmemIo<16> {
+  static __device__ __forceinline__ void ld(unsigned a, unsigned *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(a));
+  }
+  static __device__ __forceinline__ void st(unsigned a, const unsigned *r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(a),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+  }
+};
+// N words starting at column address a, in power-of-two pieces (largest first)
+template <int N>
+__device__ __forceinline__ void tmem_ld(unsigned a, unsigned (&r)[N]) {
+  static_assert(N < 32, "pieces of 16, 8, 4, 2, 1 words");
+  int done = 0;
+#pragma unroll
+  for (int p = 16; p >= 1; p >>= 1)
+    if ((N - done) >= p) {   // N < 32: every piece size occurs at most once
+      if (p == 16) TmemIo<16>::ld(a + done, r + done);
+      if (p == 8) TmemIo<8>::ld(a + done, r + done);
+      if (p == 4) TmemIo<4>::ld(a + done, r + done);
+      if (p == 2) TmemIo<2>::ld(a + done, r + done);
+      if (p == 1) TmemIo<1>::ld(a + done, r + done);
+      done += p;
+    }
+}
+template <int N>
+__device__ __forceinline__ void tmem_st(unsigned a, const unsigned (&r)[N]) {
+  static_assert(N < 32, "pieces of 16, 8, 4, 2, 1 words");
+  int done = 0;
+#pragma unroll
+  for (int p = 16; p >= 1; p >>= 1)
+    if ((N - done) >= p) {
+      if (p == 16) TmemIo<16>::st(a + done, r + done);
+      if (p == 8) TmemIo<8>::st(a + done, r + done);
+      if (p == 4) TmemIo<4>::st(a + done, r + done);
+      if (p == 2) TmemIo<2>::st(a + done, r + done);
+      if (p == 1) TmemIo<1>::st(a + done, r + done);
+      done += p;
+    }
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+#endif  // __CUDACC__
+
 constexpr int fdr_cmax(int a, int b) { return a > b ? a : b; }
 // threads (a multiple of 32) taking part in a pass over G items done in ceil(G / threads) rounds
 #ifndef B2_FDR_TP_GREEDY
@@ -264,6 +411,14 @@ struct FdrCfg {
   // and the next block's first pass), so both hold the larger of the two layouts
   static constexpr int BUF_A = fdr_cmax(fdr_cmax(fdr_cmax(FW::E1_ELEMS, NIN), IV::E1_ELEMS), fdr_cmax(FW::E2_ELEMS, IV::E2_ELEMS));
   static constexpr int BUF_B = BUF_A;
+  // tensor-memory slot of a thread: [forward pass-3 twiddles | response bins | inverse pass-3 twiddles]
+  // (the inverse twiddles stay in global memory where the three do not fit the 32 words)
+  static constexpr int TM_F3 = 2 * FW::NP2C, TM_H = IV::RC;
+  static constexpr int TM_I3 = TM_F3 + TM_H + 2 * IV::NP2C <= 32 ? 2 * IV::NP2C : 0;
+  static constexpr int TM_WORDS = TM_F3 + TM_H + TM_I3;
+  static constexpr int TM_SLOTS = (THREADS / 32 + 3) / 4;                    // warps w and w + 4 share lanes: one 32-column slot each
+  static constexpr int TM_COLS = TM_SLOTS <= 1 ? 32 : TM_SLOTS <= 2 ? 64 : TM_SLOTS <= 4 ? 128 : 256;   // allocations are powers of two
+  static constexpr bool TM_OK = TM_WORDS <= 32 && TM_COLS * MIN_CTAS <= 512;
 };
 
 // 48000 -> 44100 family (io ratio 160/147): 2560 -> 2352 points
@@ -437,8 +592,37 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
 #endif
+  // tensor-memory slot of this thread (see tmem_* above): allocated by warp 0, filled once per CTA
+  constexpr bool TM = Cfg::TM_OK && B2_FDR_TMEM != 0;
+  __shared__ unsigned tm_base_s;
+  unsigned tm = 0;
+  if (TM) {
+    if (tau < 32) tmem_alloc(&tm_base_s, Cfg::TM_COLS);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
   if (tau == 0) s_ticket = P.counter ? atomicAdd(P.counter, 1u) - P.ticket_base : blockIdx.x;
   __syncthreads();
+  if (TM) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // address = lane << 16 | column: lanes 32 (warp % 4) .., columns 32 (warp / 4) ..
+    tm = tm_base_s + ((unsigned(tau >> 5) & 3u) << 21) + (unsigned(tau) >> 7) * 32u;
+    {
+      unsigned r[Cfg::TM_F3];
+      FW::tw3_words(tau, ftw3, r);
+      tmem_st(tm, r);
+    }
+    {
+      unsigned r[Cfg::TM_H];
+      IV::h_words(tau, H, r);
+      tmem_st(tm + Cfg::TM_F3, r);
+    }
+    if (Cfg::TM_I3) {
+      unsigned r[2 * IV::NP2C];
+      IV::tw3_words(tau, itw3, r);
+      tmem_st(tm + Cfg::TM_F3 + Cfg::TM_H, r);
+    }
+    tmem_wait_st();
+  }
 #ifdef B2_FDR_TIMING
   // debug build (scripts/build_variant.sh -DB2_FDR_TIMING=1): per-CTA timeline printed by thread 0
   unsigned long long dbg_t0 = 0;
@@ -550,15 +734,34 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
     }
     {
       C w[FW::RC];
-      FW::ld_tw3(tau, ftw3, w);
+      if (TM) {
+        unsigned r[Cfg::TM_F3];
+        tmem_ld(tm, r);
+        tmem_wait_ld();
+        FW::tw3_from_words(r, w);
+      } else {
+        FW::ld_tw3(tau, ftw3, w);
+      }
       __syncthreads();
       FW::fwd_p3(tau, bufB, bufA, w);
     }
     {
       R h[IV::RC];
       C w[IV::RC];
-      IV::ld_h(tau, H, h);
-      IV::ld_tw3(tau, itw3, w);
+      if (TM) {
+        unsigned r[Cfg::TM_H + Cfg::TM_I3];
+        tmem_ld(tm + Cfg::TM_F3, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int q = 0; q < IV::RC; ++q) h[q] = __uint_as_float(r[q]);
+        if (Cfg::TM_I3)
+          IV::tw3_from_words(r + Cfg::TM_H, w);
+        else
+          IV::ld_tw3(tau, itw3, w);
+      } else {
+        IV::ld_h(tau, H, h);
+        IV::ld_tw3(tau, itw3, w);
+      }
       __syncthreads();
       IV::template inv_p1<Cfg::NIN>(tau, bufA, h, bufB, w);
     }
@@ -665,6 +868,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
   // next chunk: its ticket was drawn at the start of this one (the atomic's latency is long gone)
   if (tau == 0) s_ticket = next_ticket;
   __syncthreads();
+  }
+  if (TM) {
+    // every thread left the loop behind the same barrier; no tcgen05.ld is in flight (each was waited for)
+    if (tau < 32) tmem_dealloc(tm_base_s, Cfg::TM_COLS);
   }
 #ifdef B2_FDR_TIMING
   if (tau == 0) {
