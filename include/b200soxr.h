@@ -51,7 +51,7 @@ enum {
 #define B200SOXR_ROLLOFF_NONE     2u
 #define B200SOXR_HI_PREC_CLOCK    8u
 #define B200SOXR_DOUBLE_PRECISION 16u
-#define B200SOXR_VR               32u   /* not supported: create fails */
+#define B200SOXR_VR               32u   /* variable-rate engine (vr32.c); ratio changes via b200soxr_set_io_ratio */
 
 /* Layout-compatible with soxr_io_spec_t (soxr.h:226-232). */
 typedef struct b200soxr_io_spec {
@@ -123,6 +123,12 @@ B200SOXR_API double b200soxr_delay(b200soxr_t p);
 B200SOXR_API size_t *b200soxr_num_clips(b200soxr_t p);
 B200SOXR_API char const *b200soxr_engine(b200soxr_t p);
 B200SOXR_API b200soxr_error_t b200soxr_clear(b200soxr_t p);
+
+/* Replaces soxr_set_io_ratio (libsoxr/src/soxr.h:170-172, soxr.c:579-598; bound at src/soxr_ext.cpp:200-203).
+ * A handle created with quality_spec.flags & B200SOXR_VR (its create-time in/out rates give the MAXIMUM I/O ratio,
+ * vr32.c:618-627) takes the new ratio from the next output on, or glides to it over `slew_len` output samples.
+ * Any other handle accepts only its own ratio, with the reference's error string otherwise. */
+B200SOXR_API b200soxr_error_t b200soxr_set_io_ratio(b200soxr_t p, double io_ratio, size_t slew_len);
 B200SOXR_API void b200soxr_delete(b200soxr_t p);
 
 /* ---- one-shot: soxr_oneshot (soxr.h:188-198, soxr.c:816-838) --------------- */
@@ -197,6 +203,14 @@ B200SOXR_API size_t b200soxr_plan_dump(double input_rate, double output_rate, un
  * bytes needed. */
 B200SOXR_API size_t b200soxr_describe_path(double input_rate, double output_rate, unsigned long quality, int dtype,
                                            char *buf, size_t buf_size);
+
+/* Pure-host emulation of the variable-rate engine's control flow (vr32.c:340-570): step i optionally sets a new
+ * ratio (io_ratio[i] > 0, over slew_len[i] output samples), appends ilen[i] frames, optionally starts the flush
+ * (flush[i] != 0) and asks for olen[i] frames; odone[i] = frames the reference's soxr_process call would return.
+ * Works without a GPU. */
+B200SOXR_API b200soxr_error_t b200soxr_vr_emulate(double max_io_ratio, size_t n_steps, double const *io_ratio,
+                                                  size_t const *slew_len, size_t const *ilen,
+                                                  unsigned char const *flush, size_t const *olen, size_t *odone);
 
 /* Pure-host emulation of the reference's pull scheduler (cr.c:498-581): number of
  * output frames each soxr_process call of the given chunk partition returns.

@@ -87,6 +87,8 @@ def lib():
         L.soxr_engine.argtypes = [C.c_void_p]
         L.soxr_clear.restype = C.c_char_p
         L.soxr_clear.argtypes = [C.c_void_p]
+        L.soxr_set_io_ratio.restype = C.c_char_p
+        L.soxr_set_io_ratio.argtypes = [C.c_void_p, C.c_double, C.c_size_t]
         L.soxr_delete.restype = None
         L.soxr_delete.argtypes = [C.c_void_p]
         _lib = L
@@ -222,7 +224,11 @@ class RefStream:
     """Mirrors class CSoxr (soxr_ext.cpp:49-205) + ResampleStream (__init__.py:61-179)."""
 
     def __init__(self, in_rate, out_rate, num_channels, dtype='float32', quality='HQ',
-                 io_flags=0, q_flags=0):
+                 io_flags=0, q_flags=0, vr=False):
+        if vr:
+            q_flags |= 32      # SOXR_VR, soxr.h:254 (soxr_ext.cpp:74)
+        self._vr = vr
+        self._ybytes = 0
         self._type = np.dtype(dtype)
         self._t = _dt(self._type)
         self._ch = num_channels
@@ -269,6 +275,72 @@ class RefStream:
                 out_pos += odone.value
                 if odone.value == 0:
                     break
+        y = y[:out_pos].copy()
+        return y[:, 0] if squeeze else y
+
+    def set_io_ratio(self, in_rate, out_rate, slew_len=0):
+        """__init__.py:162-179 -> soxr_ext.cpp:200-203"""
+        err = lib().soxr_set_io_ratio(self._h, in_rate / out_rate, slew_len)
+        if err:
+            raise RuntimeError(err.decode())
+
+    def _olen_buf(self, fsz, req_len=None):
+        """_resize_ybuf (soxr_ext.cpp:89-107): frames the binding's reusable buffer holds"""
+        if req_len is None:
+            self._ybytes *= 2
+        else:
+            req = fsz * req_len
+            if not (self._ybytes and req < self._ybytes):
+                n = 1024
+                while n < req:
+                    n <<= 1
+                self._ybytes = n
+        return self._ybytes // fsz
+
+    def process_vr(self, x, last=False):
+        """CSoxr::process exactly as the binding drives it (soxr_ext.cpp:129-188), including the size of the
+        reusable output buffer and the mid-call pulls of variable-rate mode (:170-173): what a variable-rate
+        stream returns per call depends on the room each soxr_process call is offered."""
+        L = lib()
+        squeeze = x.ndim == 1
+        if squeeze:
+            x = x[:, None]
+        x = np.ascontiguousarray(x)
+        if self._ended:
+            raise RuntimeError("Input after last input")
+        ilen, ch = x.shape
+        isz = x.dtype.itemsize * ch
+        olen = self._olen_buf(isz, int(L.soxr_delay(self._h) + ilen * self._oi + 1))
+        y = np.zeros((olen, ch), dtype=x.dtype)
+        out_pos = 0
+        odone = C.c_size_t(0)
+
+        def pull(in_ptr):
+            nonlocal y, olen, out_pos
+            while True:
+                if olen <= out_pos:
+                    new_olen = self._olen_buf(isz)
+                    y = np.concatenate([y, np.zeros((new_olen - olen, ch), dtype=x.dtype)])
+                    olen = new_olen
+                err = L.soxr_process(self._h, in_ptr, 0, None, y.ctypes.data + out_pos * isz, olen - out_pos,
+                                     C.byref(odone))
+                if err:
+                    raise RuntimeError(err.decode())
+                out_pos += odone.value
+                if odone.value == 0:
+                    break
+
+        for idx in range(0, ilen, self._div_len):
+            err = L.soxr_process(self._h, x.ctypes.data + idx * isz, min(self._div_len, ilen - idx), None,
+                                 y.ctypes.data + out_pos * isz, olen - out_pos, C.byref(odone))
+            if err:
+                raise RuntimeError(err.decode())
+            out_pos += odone.value
+            if olen <= out_pos:
+                pull(x.ctypes.data + idx * isz)
+        if last:
+            self._ended = True
+            pull(None)
         y = y[:out_pos].copy()
         return y[:, 0] if squeeze else y
 

@@ -23,6 +23,7 @@
 #include "plan.h"
 #include "fft_stage.cuh"
 #include "runtime.h"
+#include "vr.h"
 
 using namespace b2;
 
@@ -133,6 +134,8 @@ struct b200soxr {
   bool low_latency = false;   // B200SOXR_RT_LOW_LATENCY: direct-form kernels, every output whose support has arrived
   std::shared_ptr<DevicePlan> dp;
   std::unique_ptr<CallEmu> emu;
+  std::unique_ptr<VrEngine> vr;   // quality_spec.flags & B200SOXR_VR: the variable-rate engine (vr.h) instead of a plan
+  double vr_scale = 1;
   Workspace *ws = nullptr;
   cudaStream_t stream = nullptr;
   // Input history, one of two homes:
@@ -371,6 +374,27 @@ b200soxr_error_t b200soxr_emulate_calls(double in_rate, double out_rate, unsigne
   return nullptr;
 }
 
+// Control flow of the variable-rate engine without a device (host-side tests pin it against the live reference):
+// step i optionally changes the ratio (io_ratio[i] > 0), appends ilen[i] frames, optionally starts the flush, and
+// asks for olen[i] frames; odone[i] is what the reference's soxr_process would return.
+b200soxr_error_t b200soxr_vr_emulate(double max_io_ratio, size_t n_steps, double const *io_ratio,
+                                     size_t const *slew_len, size_t const *ilen, unsigned char const *flush,
+                                     size_t const *olen, size_t *odone) {
+  if (!(max_io_ratio > 0)) return "I/O ratio out-of-range";
+  VrEngine vr(max_io_ratio, 1.0, 1);
+  vr.set_dry_run();
+  if (const char *e = vr.init()) return e;
+  for (size_t i = 0; i < n_steps; ++i) {
+    if (io_ratio && io_ratio[i] > 0) vr.set_io_ratio(io_ratio[i], slew_len ? slew_len[i] : 0);
+    if (ilen && ilen[i]) if (const char *e = vr.dry_input(ilen[i])) return e;
+    if (flush && flush[i]) vr.flush();
+    size_t od = 0;
+    if (const char *e = vr.process(olen[i], nullptr, 0, &od, nullptr)) return e;
+    if (odone) odone[i] = od;
+  }
+  return nullptr;
+}
+
 static b200soxr_t create_handle(double input_rate, double output_rate, unsigned n_streams, unsigned num_channels,
                                 b200soxr_error_t *error0, b200soxr_io_spec_t const *io_spec,
                                 b200soxr_quality_spec_t const *q_spec, b200soxr_runtime_spec_t const *rt_spec) {
@@ -405,7 +429,16 @@ static b200soxr_t create_handle(double input_rate, double output_rate, unsigned 
     unsigned long long bits;
     std::memcpy(&bits, &io_ratio, 8);
     p->seed = num_channels ^ bits;
-    if (!error) error = get_device_plan(io_ratio, p->q, p->r, scale, arith_double_for(p->q, p->io.itype, p->io.otype), &p->dp);
+    const bool want_vr = (p->q.flags & B200SOXR_VR) != 0;     // soxr.c:443-455: SOXR_VR selects the vr32 engine
+    if (!error && want_vr && (p->device_io || p->low_latency))
+      error = "b200soxr: variable-rate handles take host buffers and the reference's scheduling only";
+    if (!error && !want_vr)
+      error = get_device_plan(io_ratio, p->q, p->r, scale, arith_double_for(p->q, p->io.itype, p->io.otype), &p->dp);
+    if (!error && want_vr) {
+      p->vr_scale = scale;
+      p->vr.reset(new (std::nothrow) VrEngine(io_ratio, scale, n_streams * num_channels));
+      error = p->vr ? p->vr->init() : "malloc failed";
+    }
     if (!error) {
       p->ws = acquire_workspace();
       p->stream = (rt_spec && rt_spec->e) ? static_cast<cudaStream_t>(rt_spec->e) : p->ws->stream;
@@ -413,7 +446,7 @@ static b200soxr_t create_handle(double input_rate, double output_rate, unsigned 
       if (!error) error = p->seed_dev.reserve(8 * size_t(n_streams));
       if (!error && cudaMemset(p->clips_dev.p, 0, 8) != cudaSuccess) error = "cudaMemset failed";
       if (!error) error = p->reset_seeds(p->seed);
-      if (!error) error = p->init_state();
+      if (!error && !want_vr) error = p->init_state();
     }
     if (error) { delete p; p = nullptr; }
   }
@@ -434,6 +467,7 @@ b200soxr_t b200soxr_create_batch(double input_rate, double output_rate, unsigned
 }
 
 double b200soxr_delay(b200soxr_t p) {
+  if (p && !p->error && p->vr) return 100;   // vr_delay is a constant in the reference (vr32.c:612-616, "TODO")
   if (!p || p->error || !p->emu) return 0;
   if (!p->low_latency) return p->emu->delay();
   // cr.c:578-581 with this mode's own output count: samples_in / io_ratio - samples_out before the flush,
@@ -442,7 +476,17 @@ double b200soxr_delay(b200soxr_t p) {
   return double(p->x_hi) / p->io_ratio - double(p->out_done);
 }
 size_t *b200soxr_num_clips(b200soxr_t p) { return &p->clips; }
-char const *b200soxr_engine(b200soxr_t p) { return p->dp->is_double ? "b200-cr64" : "b200-cr32"; }
+char const *b200soxr_engine(b200soxr_t p) { return p->vr ? "b200-vr32" : p->dp->is_double ? "b200-cr64" : "b200-cr32"; }
+
+// soxr_set_io_ratio (soxr.c:579-598) on a live handle: the variable-rate engine takes the new ratio, reached over
+// `slew_len` output samples (0: at once); a constant-rate handle accepts only its own ratio.
+b200soxr_error_t b200soxr_set_io_ratio(b200soxr_t p, double io_ratio, size_t slew_len) {
+  if (!p) return "invalid soxr_t pointer";
+  if (p->error) return p->error;
+  if (!(io_ratio > 0)) return "I/O ratio out-of-range";
+  if (p->vr) { p->vr->set_io_ratio(io_ratio, slew_len); return nullptr; }
+  return std::fabs(p->io_ratio - io_ratio) < 1e-15 ? nullptr : "varying O/I ratio is not supported with this quality level";
+}
 
 size_t b200soxr_describe_path(double input_rate, double output_rate, unsigned long quality, int dtype,
                               char *buf, size_t buf_size) {
@@ -475,6 +519,11 @@ b200soxr_error_t b200soxr_clear(b200soxr_t p) {
   // the device-side accumulators k_rint_clip / k_dither_seeds add to restart as well
   if (p->clips_dev.p) B2_CUDA(cudaMemsetAsync(p->clips_dev.p, 0, 8, p->stream));
   if (const char *e = p->reset_seeds(0)) return e;
+  if (p->vr) {   // RESET_ON_CLEAR: a fresh engine at the create-time (maximum) ratio (soxr.c:609-628)
+    p->flushing = false;
+    p->vr.reset(new (std::nothrow) VrEngine(p->io_ratio, p->vr_scale, p->n_sig()));
+    return p->vr ? p->vr->init() : "malloc failed";
+  }
   return p->init_state();
 }
 
@@ -493,6 +542,76 @@ static const size_t kDirectReadBytes = [] {
   return size_t(v ? std::max(0L, std::atol(v)) : 192) << 10;
 }();
 
+// One soxr_process call of a variable-rate handle (soxr.c:640-733 over vr32.c): append the input behind stage 0,
+// let the engine produce what it can of `olen` frames, convert out (K7, with the reference's dither for int16).
+static b200soxr_error_t process_vr(b200soxr_t p, void const *in, size_t ilen, size_t *idone0, void *out, size_t olen,
+                                   size_t *odone0) {
+  const unsigned ch = p->channels, B = p->n_streams, ns = p->n_sig();
+  const bool split = (p->io.itype & B200SOXR_SPLIT) != 0;
+  const int it = p->io.itype & 3, ot = p->io.otype & 3;
+  const size_t isz = dtype_size(it), osz = dtype_size(ot);
+  cudaStream_t st = p->stream;
+  Workspace *ws = p->ws;
+  const char *e = nullptr;
+  if (ilen) {
+    IoLayout lay;
+    lay.dtype = it; lay.n_clips = B; lay.channels = ch; lay.clip_stride = (long long)(ilen * ch);
+    if ((e = ws->in_stage.reserve(ilen * ch * isz * B))) return p->error = e;
+    if (split) {
+      const void *const *ptrs = static_cast<const void *const *>(in);
+      for (unsigned c = 0; c < ch; ++c)
+        B2_CUDA(cudaMemcpyAsync(static_cast<char *>(ws->in_stage.p) + size_t(c) * ilen * isz, ptrs[c], ilen * isz,
+                                cudaMemcpyHostToDevice, st));
+      lay.frame_stride = 1; lay.chan_stride = (long long)ilen;
+    } else {
+      B2_CUDA(cudaMemcpyAsync(ws->in_stage.p, in, ilen * ch * isz * B, cudaMemcpyHostToDevice, st));
+      lay.frame_stride = ch; lay.chan_stride = 1;
+    }
+    if ((e = p->vr->input(lay, ws->in_stage.p, ilen, st))) return p->error = e;
+  }
+  if (p->flushing) p->vr->flush();
+  const size_t ys = (std::max<size_t>(olen, 1) + 63) & ~size_t(63);
+  if ((e = ws->y.reserve(ys * ns * sizeof(float)))) return p->error = e;
+  size_t odone = 0;
+  if ((e = p->vr->process(olen, ws->y.as<float>(), ys, &odone, st))) return p->error = e;
+  const bool dith = ot == B200SOXR_INT16 && !(p->io.flags & B200SOXR_NO_DITHER);
+  if (odone || dith) {
+    IoLayout lay;
+    lay.dtype = ot; lay.n_clips = B; lay.channels = ch; lay.clip_stride = (long long)(odone * ch);
+    if (split) { lay.frame_stride = 1; lay.chan_stride = (long long)odone; }
+    else { lay.frame_stride = ch; lay.chan_stride = 1; }
+    if ((e = ws->out_stage.reserve(std::max<size_t>(1, odone * ch * B) * osz))) return p->error = e;
+    DitherCfg dc;
+    dc.enabled = dith;
+    dc.split = split;
+    dc.seed_in_dev = p->seed_dev.as<unsigned long long>();
+    dc.call_lens.push_back((long long)odone);
+    dc.seed_end_dev = p->seed_dev.as<unsigned long long>();
+    if ((e = convert_out(lay, ws->out_stage.p, 0, odone, false, ws->y.p, ys, dc, p->clips_dev.as<unsigned long long>(), ws, st)))
+      return p->error = e;
+    if (odone) {
+      if (split) {
+        void *const *ptrs = static_cast<void *const *>(out);
+        for (unsigned c = 0; c < ch; ++c)
+          B2_CUDA(cudaMemcpyAsync(ptrs[c], static_cast<char *>(ws->out_stage.p) + size_t(c) * odone * osz, odone * osz,
+                                  cudaMemcpyDeviceToHost, st));
+      } else {
+        B2_CUDA(cudaMemcpyAsync(out, ws->out_stage.p, odone * ch * osz * B, cudaMemcpyDeviceToHost, st));
+      }
+    }
+    if (ot >= B200SOXR_INT32) {
+      unsigned long long host = 0;
+      B2_CUDA(cudaMemcpyAsync(&host, p->clips_dev.p, 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaStreamSynchronize(st));
+      p->clips = size_t(host);
+    }
+  }
+  B2_CUDA(cudaStreamSynchronize(st));
+  if (idone0) *idone0 = ilen;
+  if (odone0) *odone0 = odone;
+  return nullptr;
+}
+
 b200soxr_error_t b200soxr_process(b200soxr_t p, void const *in, size_t ilen0, size_t *idone0, void *out,
                                   size_t olen, size_t *odone0) {
   if (!p) return "null pointer";
@@ -507,6 +626,7 @@ b200soxr_error_t b200soxr_process(b200soxr_t p, void const *in, size_t ilen0, si
   }
   p->flushing |= (ilen == ilen0 && flush_requested);
   if (!out && olen) return p->error = "null output buffer pointer";
+  if (p->vr) return process_vr(p, in, ilen, idone0, out, olen, odone0);
 
   const unsigned ch = p->channels, B = p->n_streams, ns = p->n_sig();
   const bool split = (p->io.itype & B200SOXR_SPLIT) != 0;

@@ -61,7 +61,8 @@ class ResampleStream:
 
     Parameters: in_rate, out_rate (Hz, > 0), num_channels, dtype (float32 /
     float64 / int16 / int32), quality (QQ..VHQ or their names).  `vr=True`
-    (variable rate) is not provided by the B200 library and raises.
+    selects the variable-rate engine (the constructor's rates then give the MAXIMUM in/out ratio;
+    `set_io_ratio` changes it between chunks, at once or over `slew_len` output samples).
     """
 
     def __init__(self, in_rate, out_rate, num_channels, dtype='float32', quality='HQ', vr=False, low_latency=False):

@@ -96,6 +96,8 @@ def _load():
     L.b200soxr_engine.argtypes = [C.c_void_p]
     L.b200soxr_clear.restype = C.c_char_p
     L.b200soxr_clear.argtypes = [C.c_void_p]
+    L.b200soxr_set_io_ratio.restype = C.c_char_p
+    L.b200soxr_set_io_ratio.argtypes = [C.c_void_p, C.c_double, C.c_size_t]
     L.b200soxr_delete.restype = None
     L.b200soxr_delete.argtypes = [C.c_void_p]
     L.b200soxr_resample_batch.restype = C.c_char_p
@@ -247,6 +249,23 @@ class CSoxr:
             raise RuntimeError(err.value.decode())
         self._odone = C.c_size_t(0)
         self._odone_ref = C.byref(self._odone)
+        self._vr = bool(vr)
+        self._ybytes = 0      # variable-rate handles: size of the reference's reusable output buffer (see _vr_olen)
+
+    def _vr_olen(self, req_len=None):
+        """Frames the reference binding's reusable output buffer holds (soxr_ext.cpp:89-107): it only ever grows,
+        to the next power of two of the request, or doubles (req_len None).  The variable-rate engine's output
+        of a call depends on the room it is offered, so a drop-in has to offer the same."""
+        if req_len is None:
+            self._ybytes *= 2
+        else:
+            req = self._fsz * req_len
+            if not (self._ybytes and req < self._ybytes):
+                n = 1024
+                while n < req:
+                    n <<= 1
+                self._ybytes = n
+        return self._ybytes // self._fsz
 
     def __del__(self, _delete=_lib.b200soxr_delete):   # (bound at definition: module globals may be gone at exit)
         h = getattr(self, "_h", None)
@@ -273,6 +292,8 @@ class CSoxr:
         x_addr = x.__array_interface__['data'][0]      # (ndarray.ctypes builds a helper object per access: 3x slower)
         # lowest-latency sizing of the reference (soxr_ext.cpp:155-158)
         olen = int(_lib.b200soxr_delay(h) + ilen * self._oi_ratio + 1)
+        if self._vr:
+            olen = self._vr_olen(olen)
         odone = self._odone
         if B > 1:
             return self._process_batch(x, x_addr, ilen, olen, last)
@@ -285,11 +306,27 @@ class CSoxr:
             if err:
                 raise RuntimeError(err.decode())
             out_pos += odone.value
+            if olen <= out_pos:
+                # variable-rate mode can fill the buffer: keep pulling, without new input, until nothing comes
+                # (soxr_ext.cpp:170-173 -> _flush with a non-null input pointer and ilen 0)
+                while True:
+                    if olen <= out_pos:
+                        grow = (self._vr_olen() - olen) if self._vr else max(olen, 1024)
+                        y = np.concatenate([y[:out_pos], np.empty((olen - out_pos + grow, self.channels), dtype=self._dtype)])
+                        y_addr = y.__array_interface__['data'][0]
+                        olen = y.shape[0]
+                    err = process(h, x_addr + idx * fsz, 0, None, y_addr + out_pos * fsz, olen - out_pos, self._odone_ref)
+                    if err:
+                        raise RuntimeError(err.decode())
+                    out_pos += odone.value
+                    if odone.value == 0:
+                        break
         if last:
             self.ended = True
             while True:       # flush until no more output (soxr_ext.cpp:109-127)
                 if olen <= out_pos:
-                    y = np.concatenate([y[:out_pos], np.empty((max(olen, 1024), self.channels), dtype=self._dtype)])
+                    grow = (self._vr_olen() - olen) if self._vr else max(olen, 1024)
+                    y = np.concatenate([y[:out_pos], np.empty((olen - out_pos + grow, self.channels), dtype=self._dtype)])
                     y_addr = y.__array_interface__['data'][0]
                     olen = y.shape[0]
                 err = process(h, None, 0, None, y_addr + out_pos * fsz, olen - out_pos, self._odone_ref)
@@ -349,8 +386,10 @@ class CSoxr:
         self.ended = False
 
     def set_io_ratio(self, io_ratio, slew_len=0):
-        # variable-rate engine (vr32.c) is outside this library's scope
-        raise RuntimeError("varying O/I ratio is not supported with this quality level")
+        # soxr_ext.cpp:200-203
+        err = _lib.b200soxr_set_io_ratio(self._h, float(io_ratio), int(slew_len))
+        if err:
+            raise RuntimeError(err.decode())
 
 
 def _check_2d(x, code):
