@@ -117,8 +117,8 @@ __device__ __forceinline__ void clock_at(unsigned long long at0, unsigned long l
 // All signals share one clock, so the interpolated coefficients of output n (n_taps Horner evaluations fed by
 // n_taps * (order + 1) scattered table reads, up to 164 kB of table) are computed ONCE per thread, parked in the
 // thread's column of shared memory, and applied to `spb` signals (blockIdx.y selects the group).  The per-output
-// arithmetic is unchanged (Horner in engine precision like the reference, double accumulation), so results do
-// not depend on the grouping.
+// arithmetic is the same for every signal whatever the grouping (Horner and accumulation in engine precision like
+// the reference), so a stream's results do not depend on how it was chunked or batched.
 template <typename T>
 __global__ void k_poly_interp(SigIn<T> in, const T *__restrict__ table, int n_taps, int order,
                               int phase_bits, unsigned long long at0, unsigned long long step,
@@ -143,16 +143,49 @@ __global__ void k_poly_interp(SigIn<T> in, const T *__restrict__ table, int n_ta
   }
   const bool inside = pos >= in.vlo && pos + n_taps <= in.vhi;   // the whole window is real input: no per-tap checks
   const unsigned s_end = min(n_sig, (blockIdx.y + 1u) * spb);
-  for (unsigned s = blockIdx.y * spb; s < s_end; ++s) {
-    double acc = 0;
+  // Accumulation in engine precision with fused multiply-adds, two interleaved partial sums (the reference's SIMD
+  // engines keep four): float32 for the f32 engine -- no float->double conversion per tap on the 16-lane XU pipe,
+  // which was half of this kernel's time (profiles/r2s) -- double for the f64 engine.  Four signals share each
+  // coefficient read.
+  unsigned s = blockIdx.y * spb;
+  const int bd = int(blockDim.x);
+  if (inside) {
+    const long long fs = in.frame_stride;
+    for (; s + 4 <= s_end; s += 4) {
+      const T *__restrict__ p0 = in.sig(s) + (long long)pos * fs, *__restrict__ p1 = in.sig(s + 1) + (long long)pos * fs;
+      const T *__restrict__ p2 = in.sig(s + 2) + (long long)pos * fs, *__restrict__ p3 = in.sig(s + 3) + (long long)pos * fs;
+      T e0 = 0, o0 = 0, e1 = 0, o1 = 0, e2 = 0, o2 = 0, e3 = 0, o3 = 0;
+      int j = 0;
+      for (; j + 1 < n_taps; j += 2) {
+        const T v = vs[j * bd], w = vs[(j + 1) * bd];
+        e0 = fma(v, p0[j * fs], e0); o0 = fma(w, p0[(j + 1) * fs], o0);
+        e1 = fma(v, p1[j * fs], e1); o1 = fma(w, p1[(j + 1) * fs], o1);
+        e2 = fma(v, p2[j * fs], e2); o2 = fma(w, p2[(j + 1) * fs], o2);
+        e3 = fma(v, p3[j * fs], e3); o3 = fma(w, p3[(j + 1) * fs], o3);
+      }
+      if (j < n_taps) {
+        const T v = vs[j * bd];
+        e0 = fma(v, p0[j * fs], e0); e1 = fma(v, p1[j * fs], e1); e2 = fma(v, p2[j * fs], e2); e3 = fma(v, p3[j * fs], e3);
+      }
+      out.at(s, n) = e0 + o0;
+      out.at(s + 1, n) = e1 + o1;
+      out.at(s + 2, n) = e2 + o2;
+      out.at(s + 3, n) = e3 + o3;
+    }
+  }
+  for (; s < s_end; ++s) {     // (the same order of operations per signal as above)
+    T e = 0, o = 0;
+    int j = 0;
     if (inside) {
       const T *__restrict__ src = in.sig(s) + (long long)pos * in.frame_stride;
       const long long fs = in.frame_stride;
-      for (int j = 0; j < n_taps; ++j) acc = fma(double(vs[j * blockDim.x]), double(src[j * fs]), acc);
+      for (; j + 1 < n_taps; j += 2) { e = fma(vs[j * bd], src[j * fs], e); o = fma(vs[(j + 1) * bd], src[(j + 1) * fs], o); }
+      if (j < n_taps) e = fma(vs[j * bd], src[j * fs], e);
     } else {
-      for (int j = 0; j < n_taps; ++j) acc = fma(double(vs[j * blockDim.x]), double(in.at(s, pos + j)), acc);
+      for (; j + 1 < n_taps; j += 2) { e = fma(vs[j * bd], in.at(s, pos + j), e); o = fma(vs[(j + 1) * bd], in.at(s, pos + j + 1), o); }
+      if (j < n_taps) e = fma(vs[j * bd], in.at(s, pos + j), e);
     }
-    out.at(s, n) = T(acc);
+    out.at(s, n) = e + o;
   }
 }
 
@@ -216,12 +249,22 @@ template <> __device__ inline unsigned bits32<double>(double v) { return unsigne
 
 // One block of `n` frames produced by one reference soxr_process call.
 struct DitherBlock { long long start; long long n; };
+// the block list of a call: a few blocks travel by value in the kernel's parameters (no copy, no pinned staging
+// write on the stream: a stream chunk or a whole-clip batch has 1-4), longer lists through device memory
+struct DitherBlocksPtr {
+  const DitherBlock *p;
+  __device__ __forceinline__ DitherBlock operator[](unsigned i) const { return p[i]; }
+};
+struct DitherBlocks8 {   // (a __grid_constant__ parameter: indexed in place, not copied to the thread's stack)
+  DitherBlock b[8];
+  __device__ __forceinline__ DitherBlock operator[](unsigned i) const { return b[i]; }
+};
 
 // Sequential seed pre-pass: one thread per clip walks blocks x channels.
 // seeds[(clip*n_blocks + blk)*channels + ch] = {group-start seed, tail seed (salted, before its 2 steps)}
-template <typename T>
+template <typename T, typename BL>
 __global__ void k_dither_seeds(const T *__restrict__ Y, size_t y_stride, unsigned channels, unsigned n_clips,
-                               const DitherBlock *__restrict__ blocks, unsigned n_blocks,
+                               const __grid_constant__ BL blocks, unsigned n_blocks,
                                unsigned long long seed0, const unsigned long long *seed_in, bool split,
                                ulonglong2 *__restrict__ seeds, unsigned long long *seed_end) {
   const unsigned clip = blockIdx.x * blockDim.x + threadIdx.x;
@@ -251,23 +294,32 @@ template <int BITS> struct IntOf;
 template <> struct IntOf<16> { typedef short type; static constexpr long long vmax = 32767; };
 template <> struct IntOf<32> { typedef int type; static constexpr long long vmax = 2147483647LL; };
 
-// fistp: round to nearest even; out of range / NaN => "invalid" => saturate
+// fistp: round to nearest even; out of range / NaN => "invalid" => saturate.
+// No conversion instructions (they run on the 16-lane XU pipe, which was the busiest unit of k_rint_clip: 43 %,
+// profiles/r2s): the largest value of a two's-complement type is odd and the smallest even, so with ties to even
+// rint(d) is in range exactly for lo - .5 <= d < hi + .5; inside the range d + 1.5 * 2^52 carries rint(d) in the
+// low word of its mantissa (two's complement), rounded by the adder itself.
 template <int BITS>
-__device__ inline bool rint_sat(double d, typename IntOf<BITS>::type *dst) {
-  const double r = rint(d);
-  const double hi = double(IntOf<BITS>::vmax), lo = -hi - 1;
-  if (!(r >= lo && r <= hi)) {
+__device__ __forceinline__ bool rint_sat(double d, typename IntOf<BITS>::type *dst) {
+  const double hi = double(IntOf<BITS>::vmax) + .5, lo = -double(IntOf<BITS>::vmax) - 1.5;
+  if (!(d >= lo && d < hi)) {
     *dst = typename IntOf<BITS>::type(d > 0 ? IntOf<BITS>::vmax : -IntOf<BITS>::vmax - 1);
     return true;
   }
-  *dst = typename IntOf<BITS>::type((long long)r);
+  *dst = typename IntOf<BITS>::type(__double2loint(d + 6755399441055744.0));
   return false;
+}
+// (a - b) / 32 for two 5-bit fields, exactly, without an integer-to-double conversion: 2^47 has an ulp of 2^-5, so
+// the integer a - b + 1024 written into the low mantissa bits of 2^47 is the double 2^47 + 32 + (a - b) / 32.
+__device__ __forceinline__ double tpdf_term(unsigned long long ran1, unsigned long long ran2) {
+  const int k = int(unsigned(ran1) & 31u) - int(unsigned(ran2) & 31u);
+  return __longlong_as_double(0x42E0000000000000LL + (long long)(k + 1024)) - 140737488355360.0;
 }
 
 // One thread per (signal, block, 16-sample group); group index == n/16 is the tail.
-template <typename T, int BITS>
+template <typename T, int BITS, typename BL>
 __global__ void k_rint_clip(const T *__restrict__ Y, size_t y_stride, unsigned channels, unsigned n_sig,
-                            const DitherBlock *__restrict__ blocks, unsigned n_blocks, unsigned max_groups,
+                            const __grid_constant__ BL blocks, unsigned n_blocks, unsigned max_groups,
                             const ulonglong2 *__restrict__ seeds /* null: no dither */,
                             typename IntOf<BITS>::type *__restrict__ out, long long clip_stride,
                             long long frame_stride, long long chan_stride, long long frame_off,
@@ -319,7 +371,7 @@ __global__ void k_rint_clip(const T *__restrict__ Y, size_t y_stride, unsigned c
         double d = double(x[k]);
         if (dither) {
           ran1 >>= 3; ran2 >>= 3;
-          d = d + (1. / 32) * double(int((ran1 & 31) - (ran2 & 31)));
+          d = d + tpdf_term(ran1, ran2);
         }
         invalid |= rint_sat<BITS>(d, &v[k]);
       }
@@ -335,7 +387,7 @@ __global__ void k_rint_clip(const T *__restrict__ Y, size_t y_stride, unsigned c
           double d = double(x[k]);
           if (dither) {
             ran1 >>= 3; ran2 >>= 3;
-            d = d + (1. / 32) * double(int((ran1 & 31) - (ran2 & 31)));
+            d = d + tpdf_term(ran1, ran2);
           }
           if (rint_sat<BITS>(d, &v[k])) ++my_clips;
         }
@@ -365,7 +417,7 @@ __global__ void k_rint_clip(const T *__restrict__ Y, size_t y_stride, unsigned c
         double d = double(src[i]);
         if (dither) {
           ran1 >>= 3; ran2 >>= 3;
-          d = d + (1. / 32) * double(int((ran1 & 31) - (ran2 & 31)));
+          d = d + tpdf_term(ran1, ran2);
         }
         I v;
         if (rint_sat<BITS>(d, &v)) ++my_clips;

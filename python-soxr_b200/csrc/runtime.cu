@@ -362,17 +362,28 @@ const char *convert_out_int(const IoLayout &lay, void *out, size_t frame_off, si
   const unsigned nb = unsigned(blocks.size());
   long long max_n = 0;
   for (auto &b : blocks) max_n = std::max(max_n, b.n);
-  if (const char *e = ws->blocks.reserve(nb * sizeof(DitherBlock))) return e;
-  if (const char *e = ws->pin_misc.reserve(nb * sizeof(DitherBlock))) return e;
-  std::memcpy(ws->pin_misc.p, blocks.data(), nb * sizeof(DitherBlock));
-  B2_CUDA(cudaMemcpyAsync(ws->blocks.p, ws->pin_misc.p, nb * sizeof(DitherBlock), cudaMemcpyHostToDevice, st));
+  const bool by_value = nb <= 8;
+  DitherBlocks8 b8{};
+  DitherBlocksPtr bp{nullptr};
+  if (by_value) {
+    for (unsigned i = 0; i < nb; ++i) b8.b[i] = blocks[i];
+  } else {
+    if (const char *e = ws->blocks.reserve(nb * sizeof(DitherBlock))) return e;
+    if (const char *e = ws->pin_misc.reserve(nb * sizeof(DitherBlock))) return e;
+    std::memcpy(ws->pin_misc.p, blocks.data(), nb * sizeof(DitherBlock));
+    B2_CUDA(cudaMemcpyAsync(ws->blocks.p, ws->pin_misc.p, nb * sizeof(DitherBlock), cudaMemcpyHostToDevice, st));
+    bp.p = ws->blocks.as<DitherBlock>();
+  }
   ulonglong2 *seeds = nullptr;
   if (dc.enabled) {
     if (const char *e = ws->seeds.reserve(size_t(lay.n_clips) * nb * lay.channels * sizeof(ulonglong2))) return e;
     seeds = ws->seeds.as<ulonglong2>();
-    k_dither_seeds<T><<<(lay.n_clips + 63) / 64, 64, 0, st>>>(Y, ys, lay.channels, lay.n_clips,
-                                                            ws->blocks.as<DitherBlock>(), nb, dc.seed0, dc.seed_in_dev,
-                                                            dc.split, seeds, dc.seed_end_dev);
+    if (by_value)
+      k_dither_seeds<T, DitherBlocks8><<<(lay.n_clips + 63) / 64, 64, 0, st>>>(
+          Y, ys, lay.channels, lay.n_clips, b8, nb, dc.seed0, dc.seed_in_dev, dc.split, seeds, dc.seed_end_dev);
+    else
+      k_dither_seeds<T, DitherBlocksPtr><<<(lay.n_clips + 63) / 64, 64, 0, st>>>(
+          Y, ys, lay.channels, lay.n_clips, bp, nb, dc.seed0, dc.seed_in_dev, dc.split, seeds, dc.seed_end_dev);
     B2_COUNT_LAUNCH();
     B2_CUDA(cudaGetLastError());
   }
@@ -380,10 +391,15 @@ const char *convert_out_int(const IoLayout &lay, void *out, size_t frame_off, si
     const unsigned max_groups = unsigned(max_n / 16 + 1);
     dim3 grid((max_groups + 127) / 128, nb, std::min(n_sig, 65535u));
     if (grid.y > 65535) return "too many dither blocks";
-    k_rint_clip<T, BITS><<<grid, 128, 0, st>>>(Y, ys, lay.channels, n_sig, ws->blocks.as<DitherBlock>(), nb,
-                                                max_groups, seeds, static_cast<typename IntOf<BITS>::type *>(out),
-                                                lay.clip_stride, lay.frame_stride, lay.chan_stride,
-                                                (long long)frame_off, clips_dev);
+    typedef typename IntOf<BITS>::type I;
+    if (by_value)
+      k_rint_clip<T, BITS, DitherBlocks8><<<grid, 128, 0, st>>>(Y, ys, lay.channels, n_sig, b8, nb, max_groups, seeds,
+                                                               static_cast<I *>(out), lay.clip_stride, lay.frame_stride,
+                                                               lay.chan_stride, (long long)frame_off, clips_dev);
+    else
+      k_rint_clip<T, BITS, DitherBlocksPtr><<<grid, 128, 0, st>>>(Y, ys, lay.channels, n_sig, bp, nb, max_groups, seeds,
+                                                                 static_cast<I *>(out), lay.clip_stride, lay.frame_stride,
+                                                                 lay.chan_stride, (long long)frame_off, clips_dev);
     B2_COUNT_LAUNCH();
     B2_CUDA(cudaGetLastError());
   }
