@@ -674,7 +674,8 @@ b200soxr_error_t b200soxr_process(b200soxr_t p, void const *in, size_t ilen0, si
           // ~12 GB/s and was 0.7 of the 1.0 ms a 256-stream call took (profiles/r2d_stream_batch_percall.log).
           const size_t bytes = ilen * ch * isz * B;
           const void *h2d_src = in;
-          if (bytes >= (size_t(1) << 20)) {
+          static const bool no_staging = [] { const char *v = std::getenv("B200SOXR_NO_HOST_STAGING"); return v && v[0] == '1'; }();
+          if (bytes >= (size_t(1) << 20) && !no_staging) {
             cudaPointerAttributes pa;
             const bool pageable = cudaPointerGetAttributes(&pa, in) != cudaSuccess || pa.type == cudaMemoryTypeUnregistered;
             cudaGetLastError();
