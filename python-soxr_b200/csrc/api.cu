@@ -669,23 +669,10 @@ b200soxr_error_t b200soxr_process(b200soxr_t p, void const *in, size_t ilen0, si
                                     cudaMemcpyHostToDevice, st));
           lay.frame_stride = 1; lay.chan_stride = (long long)ilen;
         } else {
-          // A large chunk of ordinary (pageable) memory -- many lockstep streams per call -- goes through a pinned
-          // slot filled by the host copy pool: the driver's own staging of a pageable cudaMemcpyAsync runs at
-          // ~12 GB/s and was 0.7 of the 1.0 ms a 256-stream call took (profiles/r2d_stream_batch_percall.log).
-          const size_t bytes = ilen * ch * isz * B;
-          const void *h2d_src = in;
-          static const bool no_staging = [] { const char *v = std::getenv("B200SOXR_NO_HOST_STAGING"); return v && v[0] == '1'; }();
-          if (bytes >= (size_t(1) << 20) && !no_staging) {
-            cudaPointerAttributes pa;
-            const bool pageable = cudaPointerGetAttributes(&pa, in) != cudaSuccess || pa.type == cudaMemoryTypeUnregistered;
-            cudaGetLastError();
-            if (pageable) {
-              if ((e = ws->pin_in.reserve(bytes))) return p->error = e;
-              parallel_memcpy(ws->pin_in.p, in, bytes);
-              h2d_src = ws->pin_in.p;
-            }
-          }
-          B2_CUDA(cudaMemcpyAsync(ws->in_stage.p, h2d_src, bytes, cudaMemcpyHostToDevice, st));
+          // (Staging a large pageable chunk through a pinned slot with the host copy pool was measured and rejected for
+          // this path: 256 streams x 32 kB per call take 1.75 ms that way against 1.05 ms with the driver's own staging,
+          // profiles/r2v_stream_staging_rejected.log -- the pool pays off from tens of MB, as in resample_batch.)
+          B2_CUDA(cudaMemcpyAsync(ws->in_stage.p, in, ilen * ch * isz * B, cudaMemcpyHostToDevice, st));
           lay.frame_stride = ch; lay.chan_stride = 1;
         }
         dev_in = ws->in_stage.p;
