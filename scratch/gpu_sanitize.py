@@ -23,3 +23,14 @@ if len(sys.argv) > 1 and sys.argv[1] == 'multi':
         y = soxr.resample_batch(x, ir, orr, q)
         y1 = soxr.resample_batch(x[-1:], ir, orr, q)
         print('multi', ir, orr, q, ch, y.shape, 'last clip equals its single-clip result:', bool(np.all(y[-1] == y1[0])))
+# variable-rate engine: stage switches, fades, slews, int16 output
+if len(sys.argv) > 1 and sys.argv[1] in ('vr', 'multi'):
+    rs = soxr.ResampleStream(6, 1, 2, 'float32', vr=True)
+    n = 0
+    for i, (ratio, slew) in enumerate([(None, 0), (3.3, 500), (1.7, 200), (0.8, 300), (0.35, 0), (5.9, 1000), (None, 0), (None, 0)]):
+        if ratio:
+            rs.set_io_ratio(ratio, 1, slew)
+        n += rs.resample_chunk(rng.standard_normal((3000, 2)).astype(np.float32), last=(i == 7)).shape[0]
+    print('vr float32 frames', n)
+    rs = soxr.ResampleStream(3, 1, 1, 'int16', vr=True)
+    print('vr int16 frames', sum(rs.resample_chunk(np.round(rng.standard_normal(2000) * 5000).astype(np.int16), last=(i == 2)).shape[0] for i in range(3)))
