@@ -240,13 +240,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
+    # the clock sampler (nvidia-smi -lms 100) is started and given time to come up BEFORE the warm-up steps, so that
+    # nothing but a barrier separates the warm-up from the timed steps (an idle quarter second there made the first
+    # timed steps slower than the rest: kernel_ms_avg 3 % above the median)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
+    for _ in range(args.warmup):
+        step()
+    barrier()
     launches0 = soxr_ext.launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e_beg, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -413,6 +416,7 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "kernel": KERNEL_DESC, "library_sha256_16": _lib_sha(),
                      "kernel_ms_avg": k_avg, "kernel_ms_min": k_ms[0], "kernel_ms_median": k_ms[len(k_ms) // 2],
+                     "kernel_ms_each": [round(v, 4) for v in kernel_ms],
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                      "note": "kernel_ms_* = CUDA-event time of one whole step (all its launches) on the launching stream; "
                              "shared-memory/FMA bound, not HBM bound: see DESIGN.md"},
