@@ -8,6 +8,8 @@
  *   device     the same with B200SOXR_RT_DEVICE_IO (device pointers)
  *   cstream    the same on a caller-supplied cudaStream_t (runtime_spec.e)
  *   batch      b200soxr_create_batch: 3 lockstep streams through one handle
+ *   vr         quality_spec.flags |= B200SOXR_VR, 1000-frame chunks, b200soxr_set_io_ratio half-way <- soxr_set_io_ratio,
+ *              (to 0.6 of the create-time ratio over 500 output samples), flush                       soxr_ext.cpp:200-203
  *
  * usage: test_abi <mode> <in_rate> <out_rate> <channels> <quality> <in.f32> <out.f32>
  * in.f32 holds interleaved float32 frames; the result is written interleaved (for `batch`, in.f32 holds
@@ -155,6 +157,35 @@ int main(int argc, char **argv) {
       for (unsigned b = 1; b < n_streams; ++b) memmove(y + b * out_pos * ch, y + b * olen * ch, out_pos * ch * sizeof(float));
     }
     free(piece); free(cin);
+  } else if (strcmp(mode, "vr") == 0) {
+    /* variable rate: the create-time rates give the MAXIMUM I/O ratio; every call offers `room` frames of output */
+    b200soxr_io_spec_t io = b200soxr_io_spec(B200SOXR_FLOAT32_I, B200SOXR_FLOAT32_I);
+    b200soxr_quality_spec_t qv = b200soxr_quality_spec(quality, B200SOXR_VR);
+    b200soxr_error_t err = NULL;
+    b200soxr_t h = b200soxr_create(in_rate, out_rate, ch, &err, &io, &qv, NULL);
+    CHECK(err);
+    if (strcmp(b200soxr_engine(h), "b200-vr32") != 0) { fprintf(stderr, "unexpected engine %s\n", b200soxr_engine(h)); return 4; }
+    const size_t chunk = 1000, room = 8192;
+    size_t cap = olen * 2 + room;
+    float *yv = (float *)calloc(cap * ch, sizeof(float));
+    int changed = 0;
+    for (size_t idx = 0;; ) {
+      const int flush = idx >= ilen;
+      const size_t n = flush ? 0 : (ilen - idx < chunk ? ilen - idx : chunk);
+      if (!changed && idx >= ilen / 2) {
+        CHECK(b200soxr_set_io_ratio(h, 0.6 * in_rate / out_rate, 500));
+        changed = 1;
+      }
+      if (out_pos + room > cap) { cap *= 2; yv = (float *)realloc(yv, cap * ch * sizeof(float)); }
+      CHECK(b200soxr_process(h, flush ? NULL : x + idx * ch, n, NULL, yv + out_pos * ch, room, &odone));
+      out_pos += odone;
+      if (flush && odone == 0) break;
+      idx += n;
+    }
+    if (b200soxr_set_io_ratio(h, -1, 0) == NULL) { fprintf(stderr, "a negative ratio was accepted\n"); return 4; }
+    b200soxr_delete(h);
+    free(y);
+    y = yv;
   } else {
     fprintf(stderr, "unknown mode %s\n", mode);
     return 1;

@@ -65,3 +65,37 @@ def test_c_harness_batched_streams(tmp_path):
     y = _run("batch", x, 44100, 16000, 'HQ', tmp_path, n_streams=3)
     for b in range(3):
         assert np.array_equal(y[b], soxr._resample_oneshot(x[b], 44100, 16000, 'HQ'))
+
+
+def test_c_harness_variable_rate(tmp_path):
+    """`vr` mode of the harness (B200SOXR_VR + b200soxr_set_io_ratio from plain C) against the same calls made on the
+    unmodified reference through ctypes: bit for bit."""
+    import ctypes as C
+    import ref_soxr as R
+    if not R.available():
+        pytest.skip("oracle/_ref not built")
+    in_rate, out_rate, ch = 5.0, 1.0, 2
+    x = np.random.default_rng(21).standard_normal((12000, ch)).astype(np.float32)
+    y = _run("vr", x, in_rate, out_rate, 'HQ', tmp_path)
+    rl = R.lib()
+    h = R._create(in_rate, out_rate, ch, 0, 0, 'HQ', 0, 32)
+    room, chunk, ilen = 8192, 1000, x.shape[0]
+    buf = np.zeros((room, ch), np.float32)
+    od = C.c_size_t(0)
+    pieces, idx, changed = [], 0, False
+    while True:
+        flush = idx >= ilen
+        n = 0 if flush else min(chunk, ilen - idx)
+        if not changed and idx >= ilen // 2:
+            assert not rl.soxr_set_io_ratio(h, 0.6 * in_rate / out_rate, 500)
+            changed = True
+        err = rl.soxr_process(h, None if flush else x[idx:].ctypes.data, n, None, buf.ctypes.data, room, C.byref(od))
+        assert not err, err
+        pieces.append(buf[:od.value].copy())
+        if flush and od.value == 0:
+            break
+        idx += n
+    rl.soxr_delete(h)
+    want = np.concatenate(pieces)
+    assert y.shape == want.shape
+    assert np.array_equal(y, want)
