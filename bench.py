@@ -330,7 +330,7 @@ def main():
             # (soxr.distributed.resample_batch_gathered: pieces pushed into every peer's result over NVLink peer
             # mappings by the copy engines while the next piece is computed; NCCL send/receive where there is no peer access)
             from soxr import distributed as sdist
-            msg = timed(lambda: sdist.resample_batch_gathered(x, IN_RATE, OUT_RATE, QUALITY, sub_batches=4), 5, warm=2)
+            msg = timed(lambda: sdist.resample_batch_gathered(x, IN_RATE, OUT_RATE, QUALITY, sub_batches=2), 5, warm=2)
             recv = (world - 1) * N_CLIPS * out_frames * CH * 4
             extra["weak_with_overlapped_all_gather"] = {
                 "ms_per_step": msg, "value_msamples_s": world * in_samples / (msg * 1e-3) / 1e6,

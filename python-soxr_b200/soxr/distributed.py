@@ -160,7 +160,7 @@ def _symmetric_result(shape, dtype, device, group):
     return entry
 
 
-def resample_batch_gathered(x_local, in_rate, out_rate, quality='HQ', sub_batches=4, group=None, _compute=None,
+def resample_batch_gathered(x_local, in_rate, out_rate, quality='HQ', sub_batches=2, group=None, _compute=None,
                             method='auto'):
     """Resample this rank's clips and gather the outputs on every rank, overlapped: returns [world * n_local, ...].
 
