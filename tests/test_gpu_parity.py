@@ -543,3 +543,25 @@ def test_describe_path_names_the_kernels():
     assert 'k_fdr[3528 -> 2560' in soxr_ext.describe_path(44100, 32000, soxr.HQ, 'float32')
     assert 'k_poly_interp' in soxr_ext.describe_path(44100, 47999.5, soxr.VHQ, 'float32')
     assert 'same as exact grid' in soxr_ext.describe_path(44100, 47999.5, soxr.VHQ, 'float32')
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,in_rate,out_rate,quality", [("float32", 48000, 44100, "VHQ"), ("int16", 96000, 48000, "HQ")])
+def test_pageable_host_batches_equal_pinned_and_device(dtype, in_rate, out_rate, quality):
+    """A host batch large enough for the chunked H2D -> compute -> D2H pipeline (several 16 MB chunks): ordinary
+    pageable arrays go through the pinned slots of the host copy pool (non-temporal copies), page-locked arrays are
+    DMA'd in place, torch CUDA tensors stay on the device -- the three must agree bit for bit."""
+    import torch
+    rng = np.random.default_rng(17)
+    n, frames = 260, 24000
+    if dtype == "float32":
+        x = rng.standard_normal((n, frames, 2)).astype(np.float32)
+    else:
+        x = np.round(rng.standard_normal((n, frames)) * 5000).astype(np.int16)
+    y_page = soxr.resample_batch(x, in_rate, out_rate, quality)
+    xp = torch.from_numpy(x).pin_memory().numpy()
+    yp = torch.empty(y_page.shape, dtype=torch.from_numpy(y_page).dtype).pin_memory().numpy()
+    soxr.resample_batch(xp, in_rate, out_rate, quality, out=yp)
+    y_dev = soxr.resample_batch(torch.from_numpy(x).cuda(), in_rate, out_rate, quality).cpu().numpy()
+    assert np.array_equal(y_page, yp)
+    assert np.array_equal(y_page, y_dev)
