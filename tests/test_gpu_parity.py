@@ -553,7 +553,7 @@ def test_pageable_host_batches_equal_pinned_and_device(dtype, in_rate, out_rate,
     DMA'd in place, torch CUDA tensors stay on the device -- the three must agree bit for bit."""
     import torch
     rng = np.random.default_rng(17)
-    n, frames = 260, 24000
+    n, frames = 260, (24000 if dtype == "float32" else 48000)      # 50 MB / 25 MB in: several chunks
     if dtype == "float32":
         x = rng.standard_normal((n, frames, 2)).astype(np.float32)
     else:
