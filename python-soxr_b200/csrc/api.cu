@@ -389,7 +389,8 @@ b200soxr_error_t b200soxr_vr_emulate(double max_io_ratio, size_t n_steps, double
     if (ilen && ilen[i]) if (const char *e = vr.dry_input(ilen[i])) return e;
     if (flush && flush[i]) vr.flush();
     size_t od = 0;
-    if (const char *e = vr.process(olen[i], nullptr, 0, &od, nullptr)) return e;
+    vr.plan(olen[i], &od);
+    if (const char *e = vr.run(nullptr, 0, nullptr)) return e;
     if (odone) odone[i] = od;
   }
   return nullptr;
@@ -570,10 +571,11 @@ static b200soxr_error_t process_vr(b200soxr_t p, void const *in, size_t ilen, si
     if ((e = p->vr->input(lay, ws->in_stage.p, ilen, st))) return p->error = e;
   }
   if (p->flushing) p->vr->flush();
-  const size_t ys = (std::max<size_t>(olen, 1) + 63) & ~size_t(63);
-  if ((e = ws->y.reserve(ys * ns * sizeof(float)))) return p->error = e;
   size_t odone = 0;
-  if ((e = p->vr->process(olen, ws->y.as<float>(), ys, &odone, st))) return p->error = e;
+  p->vr->plan(olen, &odone);       // control flow first: the scratch is sized by what the call yields, not by the room offered
+  const size_t ys = (std::max<size_t>(odone, 1) + 63) & ~size_t(63);
+  if ((e = ws->y.reserve(ys * ns * sizeof(float)))) return p->error = e;
+  if ((e = p->vr->run(ws->y.as<float>(), ys, st))) return p->error = e;
   const bool dith = ot == B200SOXR_INT16 && !(p->io.flags & B200SOXR_NO_DITHER);
   if (odone || dith) {
     IoLayout lay;

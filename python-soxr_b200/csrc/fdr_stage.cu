@@ -311,9 +311,9 @@ const char *prepare_cfg(DevicePlan *dp, int variant) {
   return nullptr;
 }
 
-template <class Cfg, bool FAST>
+template <class Cfg, int MODE>
 const char *launch_cfg_t(const FdrInfo &fi, FdrKParams P, long long n_items, cudaStream_t st, Workspace *ws) {
-  auto kern = k_fdr<Cfg, FAST>;
+  auto kern = k_fdr<Cfg, MODE>;
   int dev = 0;
   cudaGetDevice(&dev);
   // per instantiation (one set of statics per Cfg and FAST) and per device, initialised once under a mutex:
@@ -387,7 +387,12 @@ const char *launch_cfg_t(const FdrInfo &fi, FdrKParams P, long long n_items, cud
 }
 template <class Cfg>
 const char *launch_cfg(const FdrInfo &fi, const FdrKParams &P, long long n_items, cudaStream_t st, Workspace *ws) {
-  return P.fast ? launch_cfg_t<Cfg, true>(fi, P, n_items, st, ws) : launch_cfg_t<Cfg, false>(fi, P, n_items, st, ws);
+  switch (P.fast) {
+    case 1: return launch_cfg_t<Cfg, 1>(fi, P, n_items, st, ws);
+    case 2: return launch_cfg_t<Cfg, 2>(fi, P, n_items, st, ws);
+    case 3: return launch_cfg_t<Cfg, 3>(fi, P, n_items, st, ws);
+    default: return launch_cfg_t<Cfg, 0>(fi, P, n_items, st, ws);
+  }
 }
 }  // namespace
 
@@ -515,7 +520,14 @@ const char *fdr_run(const DevicePlan &dp, const FdrInfo &fi, const SigDesc &in, 
     return d.dtype == 0 && d.channels == 2 && group == 2 && d.chan_stride == 1 && d.frame_stride == 2 &&
            !(d.clip_stride & 1) && !((d.base * d.frame_stride) & 1) && !(reinterpret_cast<unsigned long long>(d.p) & 7);
   };
-  P.fast = !P.bpair && stereo_f32(in) && stereo_f32(out);
+  // block-paired mono signals, unit stride: float32 or int16 in, float32 out (the last also covers the planar float
+  // scratch in front of the integer epilogue)
+  auto mono_unit = [&](const SigDesc &d, int dtype) { return d.dtype == dtype && d.frame_stride == 1; };
+  static const bool no_mono_fast = [] { const char *v = std::getenv("B200SOXR_FDR_NO_MONO_FAST"); return v && v[0] == '1'; }();
+  P.fast = 0;
+  if (!P.bpair && stereo_f32(in) && stereo_f32(out)) P.fast = 1;
+  else if (P.bpair && !no_mono_fast && mono_unit(out, 0) && mono_unit(in, 0)) P.fast = 2;
+  else if (P.bpair && !no_mono_fast && mono_unit(out, 0) && mono_unit(in, 3)) P.fast = 3;
   P.o0 = o0;
   P.o1 = o1;
   P.H = fi.H.p;

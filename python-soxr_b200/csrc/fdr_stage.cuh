@@ -27,6 +27,8 @@
 // prime-factor compositions of 3/4/5/7 (fft_regs.cuh) -- PFFFT's radix-3/5 passes are compiled
 // out in libsoxr (pffft.c:320,424), its block sizes being powers of two.
 #pragma once
+#include <type_traits>
+
 #include "fft_regs.cuh"
 #include "fft_stage.cuh"
 
@@ -498,7 +500,9 @@ struct FdrKParams {
   SigDesc in, out;
   unsigned n_pairs, group, ppg;
   int bpair;                        // mono signals: blocks 2i and 2i+1 of ONE signal ride in the real / imaginary parts
-  int fast;                         // every pair is interleaved stereo float32 on both sides (checked on the host)
+  int fast;                         // layout class, checked on the host: 1 every pair is interleaved stereo float32 on
+                                    // both sides; 2 / 3 block-paired mono, unit-stride float32 / int16 in and unit-stride
+                                    // float32 out; 0 anything else
   long b_first;
   int n_blocks;                     // items per pair (block pairs when bpair)
   long o0, o1;
@@ -527,10 +531,11 @@ struct FdrHeadParams {
 };
 
 #ifdef __CUDACC__
-// FAST: every pair is interleaved stereo float32 on both sides (FdrKParams::fast, checked on the host) -- a separate
-// instantiation, so the other layouts (block-paired mono, strided, integer) cost the headline path neither
-// registers nor predicates.
-template <class Cfg, bool FAST>
+// MODE (FdrKParams::fast, checked on the host): 1 = every pair is interleaved stereo float32 on both sides; 2 / 3 =
+// block-paired mono signals with unit-stride float32 / int16 input and unit-stride float32 output (mono batches,
+// and the float scratch in front of the integer epilogue); 0 = any layout.  Separate instantiations, so the general
+// body's address set-up, predicates and registers cost the common shapes nothing.
+template <class Cfg, int MODE>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKParams P) {
   typedef float R;
   typedef float2 C;
@@ -555,8 +560,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
   // Per-pair state kept in registers across blocks: only what the interleaved-stereo fast path needs.  The other
   // layouts recompute their address set-up (pair_state) where they use it: at 64 registers per thread the full
   // state lived in local memory, and its reloads were 5 % of the warp stall samples (profiles/r1v).
-  constexpr bool fast = FAST;
-  const bool bpair = !FAST && P.bpair != 0;
+  constexpr bool fast = MODE == 1, mfast = MODE >= 2;
+  const bool bpair = mfast || (MODE == 0 && P.bpair != 0);
+  typedef typename std::conditional<MODE == 3, short, float>::type MIn;   // element type of a mono fast input
+  const MIn *src_m = nullptr;       // mono fast paths: the signal's logical sample 0 ...
+  float *dst_m = nullptr;           // ... and output 0
   struct PairState {
     PairIn<R> pin;
     long long ooff0, ooff1;
@@ -662,6 +670,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
       const PairState ps = pair_state(pair);
       src_pair = reinterpret_cast<const float2 *>(static_cast<const float *>(ps.pin.p) + ps.pin.off0);
       dst_pair = reinterpret_cast<float2 *>(static_cast<float *>(P.out.p) + ps.ooff0);
+      if (mfast) {
+        src_m = static_cast<const MIn *>(ps.pin.p) + ps.pin.off0;
+        dst_m = static_cast<float *>(P.out.p) + ps.ooff0;
+      }
       fresh = false;
     }
     const long b = P.b_first + (bpair ? 2 * bi : bi);
@@ -677,7 +689,22 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
       FW::template fwd_p1<Cfg::TP_F1>(tau, bufA, [&](int g, int n) { return stg[FW::S1 * n + g]; });
     } else
 #endif
-    if (bpair) {
+    if (mfast) {
+      // block-paired mono signal with unit stride: blocks b and b + 1 straight from the signal's row
+      const long vlo = P.in.vlo, vhi = P.in.vhi;
+      if (interior && kb + Cfg::ADV_IN + Cfg::NIN <= vhi) {
+        const MIn *__restrict__ src = src_m + kb;
+        FW::template fwd_p1<Cfg::TP_F1>(tau, bufA, [&](int g, int n) {
+          return make_float2(float(src[g + FW::G1 * n]), float(src[g + FW::G1 * n + Cfg::ADV_IN]));
+        });
+      } else {
+        const MIn *__restrict__ src = src_m;
+        FW::template fwd_p1<Cfg::TP_F1>(tau, bufA, [&](int g, int n) {
+          const long k0 = kb + g + FW::G1 * n, k1 = k0 + Cfg::ADV_IN;
+          return make_float2((k0 >= vlo && k0 < vhi) ? float(src[k0]) : 0.f, (k1 >= vlo && k1 < vhi) ? float(src[k1]) : 0.f);
+        });
+      }
+    } else if (bpair) {
       // one signal, two consecutive blocks: block b in the real part, block b + 1 in the imaginary part
       const PairIn<R> pin = pair_state(pair).pin;
       const bool both_in = interior && kb + Cfg::ADV_IN + Cfg::NIN <= pin.vhi && pin.fs == 1;
@@ -792,7 +819,28 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
     {
       // owned outputs: block-local o in [M_OUT, M_OUT + ADV_OUT), clipped to the requested range
       const int lo = int(max(long(Cfg::M_OUT), P.o0 - nb)), hi = int(min(long(Cfg::M_OUT + Cfg::ADV_OUT), P.o1 - nb));
-      if (bpair) {
+      if (mfast) {
+        const long nb1 = nb + Cfg::ADV_OUT;                  // block b + 1 (imaginary part)
+        const int lo1 = int(max(long(Cfg::M_OUT), P.o0 - nb1)), hi1 = int(min(long(Cfg::M_OUT + Cfg::ADV_OUT), P.o1 - nb1));
+        float *__restrict__ dst = dst_m + nb;
+        if (lo == Cfg::M_OUT && hi == Cfg::M_OUT + Cfg::ADV_OUT && lo1 == lo && hi1 == hi) {
+          // both blocks wholly owned: rows inside [M_OUT, M_OUT + ADV_OUT) need no predicate
+          IV::template inv_p3<Cfg::TP_I3>(tau, bufA, [&](int g, int n, C v) {
+            const bool row_in = IV::G1 * n >= Cfg::M_OUT && IV::G1 * (n + 1) <= Cfg::M_OUT + Cfg::ADV_OUT;
+            const int o = g + IV::G1 * n;
+            if (row_in || (o >= Cfg::M_OUT && o < Cfg::M_OUT + Cfg::ADV_OUT)) {
+              dst[o] = v.x;
+              dst[o + Cfg::ADV_OUT] = v.y;
+            }
+          });
+        } else {
+          IV::template inv_p3<Cfg::TP_I3>(tau, bufA, [&](int g, int n, C v) {
+            const int o = g + IV::G1 * n;
+            if (o >= lo && o < hi) dst[o] = v.x;
+            if (o >= lo1 && o < hi1) dst[o + Cfg::ADV_OUT] = v.y;
+          });
+        }
+      } else if (bpair) {
         const long long ooff0 = pair_state(pair).ooff0;
         const long nb1 = nb + Cfg::ADV_OUT;                  // block b + 1 (imaginary part)
         const int lo1 = int(max(long(Cfg::M_OUT), P.o0 - nb1)), hi1 = int(min(long(Cfg::M_OUT + Cfg::ADV_OUT), P.o1 - nb1));

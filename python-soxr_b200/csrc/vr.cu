@@ -480,7 +480,7 @@ void VrEngine::flush() {            // vr_flush (vr32.c:592-598); the zeros are 
   if (!flushing_) flushing_ = 2;    // 2: preload of stage 0 still owed (becomes 1 in process())
 }
 
-const char *VrEngine::process(size_t olen_, float *Y, size_t y_stride, size_t *odone_out, cudaStream_t st) {
+void VrEngine::plan(size_t olen_, size_t *odone_out) {
   ops_.clear();
   if (flushing_ == 2) { preload(0); flushing_ = 1; }
   if (default_io_ratio_ != 0) set_io_ratio(default_io_ratio_, 0);
@@ -610,7 +610,9 @@ const char *VrEngine::process(size_t olen_, float *Y, size_t y_stride, size_t *o
     for (int i = -1; i < num_stages_; ++i) std::fprintf(stderr, " %ld", stg(i).f.occ());
     std::fprintf(stderr, "\n");
   }
-  return run_ops(Y, y_stride, t_used, st);
+  t_used_ = t_used;
 }
+
+const char *VrEngine::run(float *Y, size_t y_stride, cudaStream_t st) { return run_ops(Y, y_stride, t_used_, st); }
 
 }  // namespace b2

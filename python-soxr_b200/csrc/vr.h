@@ -54,8 +54,15 @@ class VrEngine {
   // append n frames per signal (vr_input, vr32.c:572-575): K1 writes them straight behind stage 0's data
   const char *input(const IoLayout &lay, const void *dev_in, size_t n, cudaStream_t st);
   void flush();                                          // vr32.c:592-598
-  // vr_process + vr_output (vr32.c:425-590): up to olen frames per signal into planar Y[s * y_stride + i]
-  const char *process(size_t olen, float *Y, size_t y_stride, size_t *odone, cudaStream_t st);
+  // vr_process + vr_output (vr32.c:425-590) in two steps, so that the caller can size the result from the count:
+  // plan() runs the control flow of one call (up to olen frames) and returns how many frames it yields; run() then
+  // executes the planned operations, writing them to planar Y[s * y_stride + i], i < odone
+  void plan(size_t olen, size_t *odone);
+  const char *run(float *Y, size_t y_stride, cudaStream_t st);
+  const char *process(size_t olen, float *Y, size_t y_stride, size_t *odone, cudaStream_t st) {
+    plan(olen, odone);
+    return run(Y, y_stride, st);
+  }
   unsigned n_sig() const { return n_sig_; }
   // control flow only (no device): the frames per call the reference would return, for host-side tests
   void set_dry_run() { dry_ = true; }
@@ -104,6 +111,7 @@ class VrEngine {
   DevBuf tbuf_, ops_dev_, iir_, tables_;
   PinnedBuf ops_pin_;
   size_t t_stride_ = 0;
+  long long t_used_ = 0;           // elements of T the planned call needs
 };
 
 }  // namespace b2
