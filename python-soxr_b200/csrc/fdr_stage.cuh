@@ -694,6 +694,20 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
       const long vlo = P.in.vlo, vhi = P.in.vhi;
       if (interior && kb + Cfg::ADV_IN + Cfg::NIN <= vhi) {
         const MIn *__restrict__ src = src_m + kb;
+#if B2_FDR_PREFETCH
+        {
+          // pull the new part of the signal's next two blocks (2 ADV_IN samples behind this item's window) towards L2
+          // while this item is transformed: one 128-byte line per thread
+          constexpr int kPerLine = 128 / int(sizeof(MIn)), kLines = (2 * Cfg::ADV_IN + kPerLine - 1) / kPerLine;
+          static_assert(kLines <= 2 * Cfg::THREADS, "two lines per thread cover the next item");
+          const long nxt = kb + Cfg::ADV_IN + Cfg::NIN;
+          if (bi + 1 < P.n_blocks && nxt + 2 * Cfg::ADV_IN <= vhi) {
+            if (tau < kLines) asm volatile("prefetch.global.L2 [%0];" ::"l"(src_m + nxt + tau * kPerLine));
+            if (kLines > Cfg::THREADS && tau + Cfg::THREADS < kLines)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(src_m + nxt + (tau + Cfg::THREADS) * kPerLine));
+          }
+        }
+#endif
         FW::template fwd_p1<Cfg::TP_F1>(tau, bufA, [&](int g, int n) {
           return make_float2(float(src[g + FW::G1 * n]), float(src[g + FW::G1 * n + Cfg::ADV_IN]));
         });

@@ -8,5 +8,5 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
 for f in fdr_stage; do
   nvcc $FLAGS "$@" -Xptxas -v -x cu -c $C/$f.cu -o $V/obj_$NAME/$f.o 2>&1 | grep -A2 "Function properties for _ZN2b25k_fdrI" | tail -2
 done
-nvcc -shared -cudart static -o $V/$NAME.so $B/design.o $B/plan.o $B/runtime.o $B/fft_stage.o $V/obj_$NAME/fdr_stage.o $B/vr.o $B/api.o
+nvcc -shared -cudart static -o $V/$NAME.so $B/design.o $B/plan.o $B/runtime.o $B/fft_stage.o $V/obj_$NAME/fdr_stage.o $B/fdr_stage_mono.o $B/vr.o $B/api.o
 echo built $V/$NAME.so

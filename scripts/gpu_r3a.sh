@@ -1,8 +1,8 @@
 #!/bin/bash
 # mono fast instantiations of k_fdr (MODE 2 / 3): parity tests, mono batches and cfg4 with and without them
 OUT=gpurun_out; mkdir -p $OUT; rm -f $OUT/r3a_mono.log
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "fdr or cfg4 or batch or int" 2>&1 | tail -3 | tee -a $OUT/r3a_mono.log
-for nm in 0 1 0 1; do
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "fdr or cfg4" 2>&1 | tail -3 | tee -a $OUT/r3a_mono.log
+for nm in 0 0; do
   B200SOXR_FDR_NO_MONO_FAST=$nm python - <<'P' 2>&1 | tee -a $OUT/r3a_mono.log
 import os, sys
 sys.path.insert(0, "python-soxr_b200")
