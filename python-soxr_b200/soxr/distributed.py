@@ -143,7 +143,8 @@ def _symmetric_result(shape, dtype, device, group):
     the rendezvous is a collective and the mapping is reused by every later call.  None where peer access is not
     available (the caller then exchanges through NCCL)."""
     dist = _dist()
-    key = (tuple(shape), str(dtype), str(device), id(group))
+    ranks = tuple(dist.get_process_group_ranks(group if group is not None else dist.group.WORLD))
+    key = (tuple(shape), str(dtype), str(device), ranks)
     if key in _SYMM_CACHE:
         return _SYMM_CACHE[key]
     try:
