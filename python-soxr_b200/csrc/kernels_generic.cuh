@@ -232,7 +232,9 @@ __global__ void k_convert_out_float(const T *__restrict__ Y, size_t y_stride, si
 
 __host__ __device__ inline unsigned long long lcg_next(unsigned long long s) { return B2_LCG_A * s + B2_LCG_C; }
 // seed after k LCG steps, O(log k)
-__host__ __device__ inline unsigned long long lcg_jump(unsigned long long s, unsigned long long k) {
+// k LCG steps as one affine map: seed -> ra * seed + rc (the map depends on k alone, so a thread that owns the same
+// group index in many signals builds it once)
+__host__ __device__ inline void lcg_jump_map(unsigned long long k, unsigned long long *ra_, unsigned long long *rc_) {
   unsigned long long a = B2_LCG_A, c = B2_LCG_C, ra = 1, rc = 0;
   while (k) {
     if (k & 1) { ra = ra * a; rc = rc * a + c; }
@@ -240,6 +242,12 @@ __host__ __device__ inline unsigned long long lcg_jump(unsigned long long s, uns
     a = a * a;
     k >>= 1;
   }
+  *ra_ = ra;
+  *rc_ = rc;
+}
+__host__ __device__ inline unsigned long long lcg_jump(unsigned long long s, unsigned long long k) {
+  unsigned long long ra, rc;
+  lcg_jump_map(k, &ra, &rc);
   return ra * s + rc;
 }
 
@@ -299,6 +307,14 @@ template <> struct IntOf<32> { typedef int type; static constexpr long long vmax
 // profiles/r2s): the largest value of a two's-complement type is odd and the smallest even, so with ties to even
 // rint(d) is in range exactly for lo - .5 <= d < hi + .5; inside the range d + 1.5 * 2^52 carries rint(d) in the
 // low word of its mantissa (two's complement), rounded by the adder itself.
+// the common case of rint_sat without its saturated value: a group with an out-of-range sample is redone as a whole
+// (rint-clip.h:70-73), so the first attempt only needs to know THAT one was out of range
+template <int BITS>
+__device__ __forceinline__ bool rint_try(double d, typename IntOf<BITS>::type *dst) {
+  const double hi = double(IntOf<BITS>::vmax) + .5, lo = -double(IntOf<BITS>::vmax) - 1.5;
+  *dst = typename IntOf<BITS>::type(__double2loint(d + 6755399441055744.0));
+  return !(d >= lo && d < hi);
+}
 template <int BITS>
 __device__ __forceinline__ bool rint_sat(double d, typename IntOf<BITS>::type *dst) {
   const double hi = double(IntOf<BITS>::vmax) + .5, lo = -double(IntOf<BITS>::vmax) - 1.5;
@@ -318,7 +334,7 @@ __device__ __forceinline__ double tpdf_term(unsigned long long ran1, unsigned lo
 
 // One thread per (signal, block, 16-sample group); group index == n/16 is the tail.
 template <typename T, int BITS, typename BL>
-__global__ void k_rint_clip(const T *__restrict__ Y, size_t y_stride, unsigned channels, unsigned n_sig,
+__global__ void __launch_bounds__(128, 6) k_rint_clip(const T *__restrict__ Y, size_t y_stride, unsigned channels, unsigned n_sig,
                             const __grid_constant__ BL blocks, unsigned n_blocks, unsigned max_groups,
                             const ulonglong2 *__restrict__ seeds /* null: no dither */,
                             typename IntOf<BITS>::type *__restrict__ out, long long clip_stride,
@@ -332,6 +348,9 @@ __global__ void k_rint_clip(const T *__restrict__ Y, size_t y_stride, unsigned c
   const long long full = n / 16;
   if (g > full) return;
   unsigned my_clips = 0;
+  // this thread's jump from a block's first seed to its group's: the same affine map in every signal it visits
+  unsigned long long jump_a = 1, jump_c = 0;
+  if (seeds != nullptr && g < full) lcg_jump_map(2ull * g, &jump_a, &jump_c);
   for (unsigned s = blockIdx.z; s < n_sig; s += gridDim.z) {
     const unsigned clip = s / channels, c = s % channels;
     const T *src = Y + size_t(s) * y_stride + st;
@@ -343,7 +362,7 @@ __global__ void k_rint_clip(const T *__restrict__ Y, size_t y_stride, unsigned c
       const long long i0 = g * 16;
       unsigned long long seed1 = 0, ran1 = 0, ran2 = 0;
       if (dither) {
-        seed1 = lcg_jump(sd.x, 2ull * g);
+        seed1 = jump_a * sd.x + jump_c;
         unsigned long long t = lcg_next(seed1);
         ran1 = t >> 3;
         t = lcg_next(t);
@@ -365,15 +384,38 @@ __global__ void k_rint_clip(const T *__restrict__ Y, size_t y_stride, unsigned c
         for (int k = 0; k < 16; ++k) x[k] = sp[k];
       }
       I v[16];
-      bool invalid = false;
+      // First attempt: values only.  A sample can leave the range only from within 1 (the dither is below 1) of its
+      // ends, so one comparison in the source precision, with a generous margin, says whether the exact range check
+      // (two double comparisons per sample) is needed at all; NaNs fail it too.
+      const T near_end = T(double(IntOf<BITS>::vmax) - 256.0);
+      bool maybe = false;
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
+        maybe |= !(fabs(x[k]) < near_end);
         double d = double(x[k]);
         if (dither) {
           ran1 >>= 3; ran2 >>= 3;
           d = d + tpdf_term(ran1, ran2);
         }
-        invalid |= rint_sat<BITS>(d, &v[k]);
+        v[k] = I(__double2loint(d + 6755399441055744.0));
+      }
+      bool invalid = false;
+      if (maybe) {
+        if (dither) {
+          unsigned long long t = lcg_next(seed1);
+          ran1 = t >> 3;
+          t = lcg_next(t);
+          ran2 = t >> 3;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          double d = double(x[k]);
+          if (dither) {
+            ran1 >>= 3; ran2 >>= 3;
+            d = d + tpdf_term(ran1, ran2);
+          }
+          invalid |= rint_try<BITS>(d, &v[k]);
+        }
       }
       if (invalid) {   // group redone by RINT_CLIP from the pre-group seed, re-salted (rint-clip.h:37-54,70-73)
         const long long ne = i0 + 16;

@@ -423,7 +423,12 @@ const char *convert_out_int(const IoLayout &lay, void *out, size_t frame_off, si
   }
   if (n_sig && nb) {
     const unsigned max_groups = unsigned(max_n / 16 + 1);
-    dim3 grid((max_groups + 127) / 128, nb, std::min(n_sig, 65535u));
+    // A thread keeps its group index and walks gridDim.z-strided signals (its LCG jump to that group is built once):
+    // about 24 CTAs of work per SM in all, the rest of the batch goes into the per-thread loop.
+    unsigned long long live_ctas = 0;   // per signal: CTAs that own at least one group
+    for (auto &b : blocks) live_ctas += (unsigned long long)(b.n / 16 + 1 + 127) / 128;
+    const unsigned long long want_z = (148ull * 24 + live_ctas - 1) / std::max<unsigned long long>(1, live_ctas);
+    dim3 grid((max_groups + 127) / 128, nb, unsigned(std::min<unsigned long long>(std::max<unsigned long long>(1, want_z), std::min(n_sig, 65535u))));
     if (grid.y > 65535) return "too many dither blocks";
     typedef typename IntOf<BITS>::type I;
     if (by_value)
