@@ -332,8 +332,119 @@ __device__ __forceinline__ double tpdf_term(unsigned long long ran1, unsigned lo
   return __longlong_as_double(0x42E0000000000000LL + (long long)(k + 1024)) - 140737488355360.0;
 }
 
-// One thread per (signal, block, 16-sample group); group index == n/16 is the tail.
-template <typename T, int BITS, typename BL>
+// One 16-sample dither group of one signal (LSX_RINT_CLIP's DO_16 body, rint-clip.h:66-74): v[k] for samples
+// i0 .. i0 + 15 of `src`, from the group's pre-draw seed.  Returns the clips it counted.
+template <typename T, int BITS>
+__device__ __forceinline__ unsigned k7_group(const T *__restrict__ src, long long i0, bool dither, unsigned long long seed1,
+                                             typename IntOf<BITS>::type (&v)[16]) {
+  typedef typename IntOf<BITS>::type I;
+  // the group's 16 samples: 16-byte vector loads when the layout allows (float scratch rows are 64-sample aligned,
+  // so this is the common case for whole-clip batches)
+  T x[16];
+  const T *sp = src + i0;
+  if (sizeof(T) == 4 && !(reinterpret_cast<unsigned long long>(sp) & 15)) {
+    const float4 *s4 = reinterpret_cast<const float4 *>(sp);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 t = s4[k];
+      x[4 * k] = T(t.x); x[4 * k + 1] = T(t.y); x[4 * k + 2] = T(t.z); x[4 * k + 3] = T(t.w);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) x[k] = sp[k];
+  }
+  // First attempt: values only.  A sample can leave the range only from within 1 (the dither is below 1) of its
+  // ends, so one comparison in the source precision, with a generous margin, says whether the exact range check
+  // (two double comparisons per sample) is needed at all; NaNs fail it too.
+  const T near_end = T(double(IntOf<BITS>::vmax) - 256.0);
+  bool maybe = false;
+  {
+    unsigned long long r1 = 0, r2 = 0;
+    if (dither) { r1 = lcg_next(seed1); r2 = lcg_next(r1) >> 3; r1 >>= 3; }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      maybe |= !(fabs(x[k]) < near_end);
+      double d = double(x[k]);
+      if (dither) {
+        r1 >>= 3; r2 >>= 3;
+        d = d + tpdf_term(r1, r2);
+      }
+      v[k] = I(__double2loint(d + 6755399441055744.0));
+    }
+  }
+  if (!maybe) return 0;
+  bool invalid = false;
+  {
+    unsigned long long r1 = 0, r2 = 0;
+    if (dither) { r1 = lcg_next(seed1); r2 = lcg_next(r1) >> 3; r1 >>= 3; }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      double d = double(x[k]);
+      if (dither) {
+        r1 >>= 3; r2 >>= 3;
+        d = d + tpdf_term(r1, r2);
+      }
+      invalid |= rint_try<BITS>(d, &v[k]);
+    }
+  }
+  if (!invalid) return 0;
+  // group redone by RINT_CLIP from the pre-group seed, re-salted (rint-clip.h:37-54,70-73)
+  unsigned n_clips = 0;
+  const long long ne = i0 + 16;
+  unsigned long long ran1 = 0, ran2 = 0;
+  if (dither) {
+    unsigned long long t = seed1 ^ (unsigned long long)ne ^ bits32<T>(src[ne / 2]);
+    t = lcg_next(t); ran1 = t >> 3;
+    t = lcg_next(t); ran2 = t >> 3;
+  }
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    double d = double(x[k]);
+    if (dither) {
+      ran1 >>= 3; ran2 >>= 3;
+      d = d + tpdf_term(ran1, ran2);
+    }
+    if (rint_sat<BITS>(d, &v[k])) ++n_clips;
+  }
+  return n_clips;
+}
+
+// the samples after the last whole group: one RINT_CLIP pass with one ran pair (rint-clip.h:75)
+template <typename T, int BITS>
+__device__ __forceinline__ unsigned k7_tail(const T *__restrict__ src, long long i_from, long long n, bool dither,
+                                            unsigned long long seed_tail, typename IntOf<BITS>::type *dst,
+                                            long long frame_stride) {
+  typedef typename IntOf<BITS>::type I;
+  unsigned long long ran1 = 0, ran2 = 0;
+  if (dither) {
+    unsigned long long t = lcg_next(seed_tail);
+    ran1 = t >> 3;
+    t = lcg_next(t);
+    ran2 = t >> 3;
+  }
+  unsigned n_clips = 0;
+  for (long long i = i_from; i < n; ++i) {
+    double d = double(src[i]);
+    if (dither) {
+      ran1 >>= 3; ran2 >>= 3;
+      d = d + tpdf_term(ran1, ran2);
+    }
+    I v;
+    if (rint_sat<BITS>(d, &v)) ++n_clips;
+    dst[i * frame_stride] = v;
+  }
+  return n_clips;
+}
+
+template <int BITS> struct IntPairOf;
+template <> struct IntPairOf<16> { typedef short2 type; };
+template <> struct IntPairOf<32> { typedef int2 type; };
+
+// One thread per (unit, block, 16-sample group); group index == n/16 is the tail.  A unit is one signal, or -- PAIR,
+// for interleaved outputs with an even channel count -- the two neighbouring channels (c, c + 1) of a clip, whose
+// results leave as one 4- / 8-byte element per frame (16-byte vectors for plain stereo) instead of strided 2- / 4-byte
+// stores: every channel keeps its own dither sequence, only the stores are shared.
+template <typename T, int BITS, typename BL, bool PAIR>
 __global__ void __launch_bounds__(128, 6) k_rint_clip(const T *__restrict__ Y, size_t y_stride, unsigned channels, unsigned n_sig,
                             const __grid_constant__ BL blocks, unsigned n_blocks, unsigned max_groups,
                             const ulonglong2 *__restrict__ seeds /* null: no dither */,
@@ -348,94 +459,42 @@ __global__ void __launch_bounds__(128, 6) k_rint_clip(const T *__restrict__ Y, s
   const long long full = n / 16;
   if (g > full) return;
   unsigned my_clips = 0;
+  const bool dither = seeds != nullptr;
   // this thread's jump from a block's first seed to its group's: the same affine map in every signal it visits
   unsigned long long jump_a = 1, jump_c = 0;
-  if (seeds != nullptr && g < full) lcg_jump_map(2ull * g, &jump_a, &jump_c);
-  for (unsigned s = blockIdx.z; s < n_sig; s += gridDim.z) {
+  if (dither && g < full) lcg_jump_map(2ull * g, &jump_a, &jump_c);
+  const long long i0 = (long long)g * 16;
+  constexpr unsigned SPU = PAIR ? 2u : 1u;   // signals per unit
+  for (unsigned s = blockIdx.z * SPU; s < n_sig; s += gridDim.z * SPU) {
     const unsigned clip = s / channels, c = s % channels;
     const T *src = Y + size_t(s) * y_stride + st;
     I *dst = out + clip * clip_stride + (frame_off + st) * frame_stride + c * chan_stride;
-    const bool dither = seeds != nullptr;
-    ulonglong2 sd = make_ulonglong2(0, 0);
-    if (dither) sd = seeds[(size_t(clip) * n_blocks + b) * channels + c];
+    const ulonglong2 *sdp = seeds + (size_t(clip) * n_blocks + b) * channels + c;
     if (g < full) {
-      const long long i0 = g * 16;
-      unsigned long long seed1 = 0, ran1 = 0, ran2 = 0;
-      if (dither) {
-        seed1 = jump_a * sd.x + jump_c;
-        unsigned long long t = lcg_next(seed1);
-        ran1 = t >> 3;
-        t = lcg_next(t);
-        ran2 = t >> 3;
-      }
-      // the group's 16 samples: 16-byte vector loads / stores when the layout allows (float scratch rows are
-      // 64-sample aligned, so this is the common case for whole-clip batches)
-      T x[16];
-      const T *sp = src + i0;
-      if (sizeof(T) == 4 && !(reinterpret_cast<unsigned long long>(sp) & 15)) {
-        const float4 *s4 = reinterpret_cast<const float4 *>(sp);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float4 t = s4[k];
-          x[4 * k] = T(t.x); x[4 * k + 1] = T(t.y); x[4 * k + 2] = T(t.z); x[4 * k + 3] = T(t.w);
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 16; ++k) x[k] = sp[k];
-      }
       I v[16];
-      // First attempt: values only.  A sample can leave the range only from within 1 (the dither is below 1) of its
-      // ends, so one comparison in the source precision, with a generous margin, says whether the exact range check
-      // (two double comparisons per sample) is needed at all; NaNs fail it too.
-      const T near_end = T(double(IntOf<BITS>::vmax) - 256.0);
-      bool maybe = false;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        maybe |= !(fabs(x[k]) < near_end);
-        double d = double(x[k]);
-        if (dither) {
-          ran1 >>= 3; ran2 >>= 3;
-          d = d + tpdf_term(ran1, ran2);
-        }
-        v[k] = I(__double2loint(d + 6755399441055744.0));
-      }
-      bool invalid = false;
-      if (maybe) {
-        if (dither) {
-          unsigned long long t = lcg_next(seed1);
-          ran1 = t >> 3;
-          t = lcg_next(t);
-          ran2 = t >> 3;
-        }
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          double d = double(x[k]);
-          if (dither) {
-            ran1 >>= 3; ran2 >>= 3;
-            d = d + tpdf_term(ran1, ran2);
-          }
-          invalid |= rint_try<BITS>(d, &v[k]);
-        }
-      }
-      if (invalid) {   // group redone by RINT_CLIP from the pre-group seed, re-salted (rint-clip.h:37-54,70-73)
-        const long long ne = i0 + 16;
-        if (dither) {
-          unsigned long long t = seed1 ^ (unsigned long long)ne ^ bits32<T>(src[ne / 2]);
-          t = lcg_next(t); ran1 = t >> 3;
-          t = lcg_next(t); ran2 = t >> 3;
-        }
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          double d = double(x[k]);
-          if (dither) {
-            ran1 >>= 3; ran2 >>= 3;
-            d = d + tpdf_term(ran1, ran2);
-          }
-          if (rint_sat<BITS>(d, &v[k])) ++my_clips;
-        }
-      }
+      my_clips += k7_group<T, BITS>(src, i0, dither, dither ? jump_a * sdp[0].x + jump_c : 0ull, v);
       I *dp = dst + i0 * frame_stride;
-      if (frame_stride == 1 && !(reinterpret_cast<unsigned long long>(dp) & 15)) {
+      if (PAIR) {
+        typedef typename IntPairOf<BITS>::type I2;
+        I w[16];
+        my_clips += k7_group<T, BITS>(src + y_stride, i0, dither, dither ? jump_a * sdp[1].x + jump_c : 0ull, w);
+        if (frame_stride == 2 && !(reinterpret_cast<unsigned long long>(dp) & 15)) {
+          constexpr int NV = int(32 * sizeof(I) / 16);
+          uint4 pk[NV];
+          I *pv = reinterpret_cast<I *>(pk);
+#pragma unroll
+          for (int k = 0; k < 16; ++k) { pv[2 * k] = v[k]; pv[2 * k + 1] = w[k]; }
+#pragma unroll
+          for (int k = 0; k < NV; ++k) reinterpret_cast<uint4 *>(dp)[k] = pk[k];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            I2 e;
+            e.x = v[k]; e.y = w[k];
+            *reinterpret_cast<I2 *>(dp + k * frame_stride) = e;
+          }
+        }
+      } else if (frame_stride == 1 && !(reinterpret_cast<unsigned long long>(dp) & 15)) {
         constexpr int NV = int(16 * sizeof(I) / 16);
         uint4 pk[NV];
         I *pv = reinterpret_cast<I *>(pk);
@@ -447,24 +506,9 @@ __global__ void __launch_bounds__(128, 6) k_rint_clip(const T *__restrict__ Y, s
 #pragma unroll
         for (int k = 0; k < 16; ++k) dp[k * frame_stride] = v[k];
       }
-    } else {           // tail: one RINT_CLIP pass with one ran pair (rint-clip.h:75)
-      unsigned long long ran1 = 0, ran2 = 0;
-      if (dither) {
-        unsigned long long t = lcg_next(sd.y);
-        ran1 = t >> 3;
-        t = lcg_next(t);
-        ran2 = t >> 3;
-      }
-      for (long long i = full * 16; i < n; ++i) {
-        double d = double(src[i]);
-        if (dither) {
-          ran1 >>= 3; ran2 >>= 3;
-          d = d + tpdf_term(ran1, ran2);
-        }
-        I v;
-        if (rint_sat<BITS>(d, &v)) ++my_clips;
-        dst[i * frame_stride] = v;
-      }
+    } else {
+      my_clips += k7_tail<T, BITS>(src, full * 16, n, dither, dither ? sdp[0].y : 0ull, dst, frame_stride);
+      if (PAIR) my_clips += k7_tail<T, BITS>(src + y_stride, full * 16, n, dither, dither ? sdp[1].y : 0ull, dst + chan_stride, frame_stride);
     }
   }
   if (my_clips) atomicAdd(clips, (unsigned long long)my_clips);

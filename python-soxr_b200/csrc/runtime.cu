@@ -423,22 +423,30 @@ const char *convert_out_int(const IoLayout &lay, void *out, size_t frame_off, si
   }
   if (n_sig && nb) {
     const unsigned max_groups = unsigned(max_n / 16 + 1);
-    // A thread keeps its group index and walks gridDim.z-strided signals (its LCG jump to that group is built once):
+    typedef typename IntOf<BITS>::type I;
+    // interleaved output with an even channel count: a thread takes the channel pair (c, c + 1) of its group and
+    // stores one 2-sample element per frame (k_rint_clip<PAIR>)
+    const bool pair = lay.channels % 2 == 0 && lay.chan_stride == 1 && lay.frame_stride % 2 == 0 && lay.clip_stride % 2 == 0 &&
+                      !(reinterpret_cast<unsigned long long>(out) % (2 * sizeof(I)));
+    const unsigned n_units = pair ? n_sig / 2 : n_sig;
+    // A thread keeps its group index and walks gridDim.z-strided units (its LCG jump to that group is built once):
     // about 24 CTAs of work per SM in all, the rest of the batch goes into the per-thread loop.
-    unsigned long long live_ctas = 0;   // per signal: CTAs that own at least one group
+    unsigned long long live_ctas = 0;   // per unit: CTAs that own at least one group
     for (auto &b : blocks) live_ctas += (unsigned long long)(b.n / 16 + 1 + 127) / 128;
     const unsigned long long want_z = (148ull * 24 + live_ctas - 1) / std::max<unsigned long long>(1, live_ctas);
-    dim3 grid((max_groups + 127) / 128, nb, unsigned(std::min<unsigned long long>(std::max<unsigned long long>(1, want_z), std::min(n_sig, 65535u))));
+    dim3 grid((max_groups + 127) / 128, nb, unsigned(std::min<unsigned long long>(std::max<unsigned long long>(1, want_z), std::min(n_units, 65535u))));
     if (grid.y > 65535) return "too many dither blocks";
-    typedef typename IntOf<BITS>::type I;
-    if (by_value)
-      k_rint_clip<T, BITS, DitherBlocks8><<<grid, 128, 0, st>>>(Y, ys, lay.channels, n_sig, b8, nb, max_groups, seeds,
-                                                               static_cast<I *>(out), lay.clip_stride, lay.frame_stride,
-                                                               lay.chan_stride, (long long)frame_off, clips_dev);
-    else
-      k_rint_clip<T, BITS, DitherBlocksPtr><<<grid, 128, 0, st>>>(Y, ys, lay.channels, n_sig, bp, nb, max_groups, seeds,
-                                                                 static_cast<I *>(out), lay.clip_stride, lay.frame_stride,
-                                                                 lay.chan_stride, (long long)frame_off, clips_dev);
+    I *o = static_cast<I *>(out);
+#define B2_K7_LAUNCH(BL, PAIR, blk)                                                                                       \
+    k_rint_clip<T, BITS, BL, PAIR><<<grid, 128, 0, st>>>(Y, ys, lay.channels, n_sig, blk, nb, max_groups, seeds, o,        \
+                                                        lay.clip_stride, lay.frame_stride, lay.chan_stride,               \
+                                                        (long long)frame_off, clips_dev)
+    if (by_value) {
+      if (pair) B2_K7_LAUNCH(DitherBlocks8, true, b8); else B2_K7_LAUNCH(DitherBlocks8, false, b8);
+    } else {
+      if (pair) B2_K7_LAUNCH(DitherBlocksPtr, true, bp); else B2_K7_LAUNCH(DitherBlocksPtr, false, bp);
+    }
+#undef B2_K7_LAUNCH
     B2_COUNT_LAUNCH();
     B2_CUDA(cudaGetLastError());
   }

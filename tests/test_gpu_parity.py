@@ -126,6 +126,34 @@ def test_device_k7_saturation_and_clip_count():
         assert clips == want_clips and s2 == sd
 
 
+@pytest.mark.parametrize('channels', [1, 2, 3, 4, 6])
+@pytest.mark.parametrize('out_dtype', ['int16', 'int32'])
+@pytest.mark.parametrize('src_dtype', [np.float32, np.float64])
+def test_device_k7_channel_layouts(channels, out_dtype, src_dtype):
+    # interleaved outputs with an even channel count leave k_rint_clip as channel pairs (one 4- / 8-byte element per
+    # frame, 16-byte vectors for stereo), the others sample by sample: same values, clip counts and seeds either way,
+    # with saturating samples and NaNs in whole groups, tails and at call boundaries
+    rng = np.random.default_rng(100 * channels + (out_dtype == 'int32'))
+    scale = 30000 if out_dtype == 'int16' else 2.0e9
+    n = 2000 + 16 * channels + 5
+    planar = (rng.standard_normal((channels, n)) * scale).astype(src_dtype)
+    planar[0, 17] = 1e12
+    planar[channels - 1, n - 1] = -1e12
+    planar[channels // 2, 3] = np.nan
+    planar[:, 640:700] *= 1e-3          # quiet stretch: groups that never come near the range ends
+    calls = [333, 0, 1000, n - 1333]
+    for seed in ((None, 987654321) if out_dtype == 'int16' else (None,)):
+        got, clips, s2 = soxr_ext.quantize(planar, out_dtype, call_lens=calls, seed=seed)
+        pos, outs, want_clips, sd = 0, [], 0, seed
+        for m in calls:
+            o, c, sd = O.rint_clip_interleave(np.ascontiguousarray(planar[:, pos:pos + m]), out_dtype, seed=sd)
+            outs.append(o)
+            want_clips += c
+            pos += m
+        assert np.array_equal(got, np.concatenate(outs))
+        assert clips == want_clips and s2 == sd
+
+
 # (44100, 32000) and (32000, 44100) are the reference's own pairs; the others are the ratio families of the
 # single-pass frequency-domain kernel, where the same bit-for-bit contract holds (the whole-signal drivers and
 # streams all evaluate the reference's block grid; only soxr.resample_batch uses the faster kernel by default)
