@@ -161,7 +161,9 @@ B200SOXR_API b200soxr_error_t b200soxr_oneshot(double input_rate, double output_
  *      `cuda_stream` is a cudaStream_t.  Host pointers: NULL => a private stream of the
  *      library; the call is synchronous (copies included).  Device pointers: the work
  *      is enqueued on `cuda_stream` as given (NULL => CUDA's legacy default stream) and
- *      the call returns without waiting.                                          */
+ *      the call returns without waiting -- except that an integer batch with
+ *      `clips` != NULL waits for its clip count (soxr_num_clips' figure, summed over
+ *      the clips); pass NULL to keep it asynchronous.                             */
 #define B200SOXR_BATCH_DEVICE_PTRS   1u
 #define B200SOXR_BATCH_NO_DITHER     2u
 #define B200SOXR_BATCH_DOUBLE        4u

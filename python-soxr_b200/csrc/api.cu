@@ -1040,9 +1040,10 @@ b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *d, void co
   if (!dev_ptrs) {
     B2_CUDA(cudaStreamSynchronize(st));
   } else {
-    // asynchronous return: float batches leave their work queued on the caller's stream; the pooled
-    // scratch they may still be using is fenced by Workspace::busy_ev for whoever takes it next
-    if (d->dtype <= B200SOXR_FLOAT64) {
+    // asynchronous return: the work stays queued on the caller's stream; the pooled scratch it may still be using is
+    // fenced by Workspace::busy_ev for whoever takes it next.  Integer batches whose caller asked for the clip count
+    // (clips != NULL) have waited for it above.
+    if (d->dtype <= B200SOXR_FLOAT64 || !clips) {
       if ((e = ws->mark_busy(st))) return e;
     } else B2_CUDA(cudaStreamSynchronize(st));
   }

@@ -763,6 +763,20 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
         const float2 *__restrict__ src = src_pair + kb * (pin.fs >> 1);
         const long long st2 = pin.fs >> 1;
         FW::template fwd_p1<Cfg::TP_F1>(tau, bufA, [&](int g, int n) { return src[(g + FW::G1 * n) * st2]; });
+      } else if (pin.vec16 && interior) {
+        // interleaved int16 neighbours (stereo PCM): one 32-bit load per frame, converted on the ALU / FMA pipes
+        const unsigned *__restrict__ src =
+            reinterpret_cast<const unsigned *>(static_cast<const short *>(pin.p) + pin.off0) + kb * (pin.fs >> 1);
+        const long long st2 = pin.fs >> 1;
+#if B2_FDR_PREFETCH
+        // pull the next block of this pair towards L2 while this one is transformed (one 128-byte line per thread)
+        if (st2 == 1 && bi + 1 < P.n_blocks && tau * 32 < Cfg::ADV_IN && kb + Cfg::NIN + Cfg::ADV_IN <= P.in.vhi)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(src + Cfg::NIN + tau * 32));
+#endif
+        FW::template fwd_p1<Cfg::TP_F1>(tau, bufA, [&](int g, int n) {
+          const unsigned t = src[(g + FW::G1 * n) * st2];
+          return make_float2(s16_bits_to_f32(t), s16_bits_to_f32(t >> 16));
+        });
       } else {
         FW::template fwd_p1<Cfg::TP_F1>(tau, bufA, [&](int g, int n) { return pin.load(kb + g + FW::G1 * n); });
       }
@@ -895,6 +909,17 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) k_fdr(const FdrKP
           IV::template inv_p3<Cfg::TP_I3>(tau, bufA, [&](int g, int n, C v) {
             const int o = g + IV::G1 * n;
             if (o >= lo && o < hi) dst[o * st2] = v;
+          });
+        } else if (P.out.dtype == 0 && P.out.frame_stride == 1 && ps.has1) {
+          // two unit-stride float32 rows (the planar scratch in front of the integer epilogue)
+          float *__restrict__ d0 = static_cast<float *>(P.out.p) + ps.ooff0 + nb;
+          float *__restrict__ d1 = static_cast<float *>(P.out.p) + ps.ooff1 + nb;
+          IV::template inv_p3<Cfg::TP_I3>(tau, bufA, [&](int g, int n, C v) {
+            const int o = g + IV::G1 * n;
+            if (o >= lo && o < hi) {
+              d0[o] = v.x;
+              d1[o] = v.y;
+            }
           });
         } else {
           IV::template inv_p3<Cfg::TP_I3>(tau, bufA, [&](int g, int n, C v) {

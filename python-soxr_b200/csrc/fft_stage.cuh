@@ -87,6 +87,12 @@ __host__ __device__ inline long long ceil_div_ll(long long a, long long b) {   /
   return a >= 0 ? (a + b - 1) / b : -((-a) / b);
 }
 
+// int16 -> float32 without a conversion instruction (those run on the 16-lane XU pipe): the biased sample
+// written into the low mantissa bits of 1.5 * 2^23 is the float 12582912 + 32768 + v, exactly.
+__device__ __forceinline__ float s16_bits_to_f32(unsigned v16) {   // sample in the low 16 bits, anything above
+  return __uint_as_float(0x4B400000u | ((v16 ^ 0x8000u) & 0xFFFFu)) - 12615680.0f;
+}
+
 // Per-item view of one signal pair.
 template <typename R>
 struct PairIn {
@@ -94,7 +100,7 @@ struct PairIn {
   int dtype;
   long long off0, off1, fs;
   long vlo, vhi;
-  bool has1, vec;
+  bool has1, vec, vec16;   // vec / vec16: the pair is one aligned float2 / short2 per frame (interleaved neighbours)
   typedef typename V2<R>::type C;
   __device__ __forceinline__ C load(long k) const {
     C c;
@@ -105,6 +111,10 @@ struct PairIn {
         const float2 t = *reinterpret_cast<const float2 *>(static_cast<const float *>(p) + off0 + k * fs);
         c.x = R(t.x);
         c.y = R(t.y);
+      } else if (vec16) {
+        const unsigned t = *reinterpret_cast<const unsigned *>(static_cast<const short *>(p) + off0 + k * fs);
+        c.x = R(s16_bits_to_f32(t));
+        c.y = R(s16_bits_to_f32(t >> 16));
       } else {
         c.x = ld_as<R>(p, dtype, off0 + k * fs);
         if (has1) c.y = ld_as<R>(p, dtype, off1 + k * fs);
@@ -127,8 +137,9 @@ __device__ __forceinline__ PairIn<R> make_pair_in(const SigDesc &d, unsigned s0,
                     : pi.off0;
   pi.vlo = d.vlo;
   pi.vhi = d.vhi;
-  pi.vec = d.dtype == 0 && pi.has1 && pi.off1 == pi.off0 + 1 && !(pi.off0 & 1) && !(pi.fs & 1) &&
-           !(reinterpret_cast<unsigned long long>(d.p) & 7);
+  const bool neighbours = pi.has1 && pi.off1 == pi.off0 + 1 && !(pi.off0 & 1) && !(pi.fs & 1);
+  pi.vec = d.dtype == 0 && neighbours && !(reinterpret_cast<unsigned long long>(d.p) & 7);
+  pi.vec16 = d.dtype == 3 && neighbours && !(reinterpret_cast<unsigned long long>(d.p) & 3);
   return pi;
 }
 

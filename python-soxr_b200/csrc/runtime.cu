@@ -406,6 +406,7 @@ const char *convert_out_int(const IoLayout &lay, void *out, size_t frame_off, si
     if (const char *e = ws->pin_misc.reserve(nb * sizeof(DitherBlock))) return e;
     std::memcpy(ws->pin_misc.p, blocks.data(), nb * sizeof(DitherBlock));
     B2_CUDA(cudaMemcpyAsync(ws->blocks.p, ws->pin_misc.p, nb * sizeof(DitherBlock), cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaStreamSynchronize(st));   // the pinned list is rewritten by the next call (callers may return without waiting)
     bp.p = ws->blocks.as<DitherBlock>();
   }
   ulonglong2 *seeds = nullptr;

@@ -260,7 +260,7 @@ def resample_batch(x, in_rate, out_rate, quality='HQ', out=None, stream=None, ex
         soxr_ext.resample_batch_raw(x.data_ptr(), out.data_ptr(), in_rate=in_rate, out_rate=out_rate, quality=q,
                                     dtype_code=code, n_clips=n_clips, channels=ch, ilen=ilen,
                                     in_strides=(ilen * ch, ch, 1), out_strides=(total * ch, ch, 1), olen=total,
-                                    flags=soxr_ext.BATCH_DEVICE_PTRS | flags, stream=s)
+                                    flags=soxr_ext.BATCH_DEVICE_PTRS | flags, stream=s, want_clips=False)
         return out
     x = np.ascontiguousarray(x)
     code = _to_soxr_datatype(x.dtype)

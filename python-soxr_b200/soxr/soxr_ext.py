@@ -176,14 +176,16 @@ def emulate_calls(in_rate, out_rate, quality, chunk_lens, olen_each=1 << 40, q_f
 
 
 def resample_batch_raw(in_ptr, out_ptr, *, in_rate, out_rate, quality, dtype_code, n_clips, channels, ilen,
-                       in_strides, out_strides, olen, flags=0, stream=None):
-    """Thin call into b200soxr_resample_batch with raw pointers (host or device)."""
+                       in_strides, out_strides, olen, flags=0, stream=None, want_clips=True):
+    """Thin call into b200soxr_resample_batch with raw pointers (host or device).  want_clips=False passes
+    clips=NULL: an integer batch on device pointers then returns without waiting, like a float one."""
     d = BatchDesc(in_rate, out_rate, quality, dtype_code, n_clips, channels, ilen,
                   in_strides[0], in_strides[1], in_strides[2],
                   out_strides[0], out_strides[1], out_strides[2], olen, flags)
     odone = C.c_size_t(0)
     clips = C.c_size_t(0)
-    err = _lib.b200soxr_resample_batch(C.byref(d), in_ptr, out_ptr, C.byref(odone), C.byref(clips), stream)
+    err = _lib.b200soxr_resample_batch(C.byref(d), in_ptr, out_ptr, C.byref(odone),
+                                       C.byref(clips) if want_clips else None, stream)
     if err:
         raise RuntimeError(err.decode())
     return odone.value, clips.value
