@@ -962,7 +962,148 @@ b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *d, void co
       per_chunk = std::min(per_chunk, d->n_clips);
     }
     const unsigned n_chunks = (d->n_clips + per_chunk - 1) / per_chunk;
-    if (n_chunks <= 1) {
+    // Pageable caller memory (an ordinary ndarray: the drop-in case) cannot be DMA'd directly; the driver's own
+    // staging runs at a fraction of the link.  It goes through pinned staging slots filled / drained by the host
+    // copy pool while the copy engines and the kernels work on the other slots (or pieces).
+    auto pageable = [](const void *ptr) {
+      cudaPointerAttributes pa;
+      if (cudaPointerGetAttributes(&pa, ptr) != cudaSuccess) { cudaGetLastError(); return true; }
+      return pa.type == cudaMemoryTypeUnregistered;
+    };
+    static const bool no_staging = [] { const char *v = std::getenv("B200SOXR_NO_HOST_STAGING"); return v && v[0] == '1'; }();
+    // Staging copies of a small call stay on the calling thread: waking the pool's workers costs 50-100 us of jitter
+    // on a virtualised host, more than they save below a few MB (profiles/r4f_time_split.log).
+    static const size_t kPoolMin = [] {
+      const char *v = std::getenv("B200SOXR_POOL_MIN_KB");
+      return size_t(v ? std::max(0L, std::atol(v)) : 8192) << 10;
+    }();
+    const bool pool_copies = (in_span + out_span) * isz >= kPoolMin;
+    auto hcopy = [&](void *dst, const void *src, size_t n) {
+      if (pool_copies) parallel_memcpy(dst, src, n); else std::memcpy(dst, src, n);
+    };
+    // one chunk (a single clip -- soxr.resample -- or a small batch) of at least this many bytes in + out
+    static const size_t kStageOneMin = [] {
+      const char *v = std::getenv("B200SOXR_STAGE_ONE_KB");
+      return size_t(v ? std::max(0L, std::atol(v)) : 512) << 10;
+    }();
+    // ONE clip on the reference's block grid with float output (soxr.resample / _resample_oneshot on an ndarray):
+    // the clip is cut in TIME and run like a stream fed piece by piece -- piece k + 1 is copied in while piece k's
+    // outputs (the frames the reference would return after that much input, CallEmu) are computed and copied back.
+    // The block grid is keyed on absolute positions, so the result is bit for bit the unsplit one.
+    static const size_t kTimeSplitMin = [] {
+      const char *v = std::getenv("B200SOXR_TIME_SPLIT_KB");
+      return size_t(v ? std::max(0L, std::atol(v)) : 1024) << 10;
+    }();
+    const size_t in_bytes = in_span * isz, out_bytes = out_span * isz;
+    const bool time_split = d->n_clips == 1 && (d->flags & B200SOXR_BATCH_EXACT_GRID) && !int_out && total &&
+                            d->in_chan_stride == 1 && d->in_frame_stride == (long long)d->channels &&
+                            d->out_chan_stride == 1 && d->out_frame_stride == (long long)d->channels &&
+                            in_bytes >= kTimeSplitMin && in_bytes + out_bytes <= (size_t(1) << 30);
+    if (time_split) {
+      const unsigned ch = d->channels;
+      const size_t fsz = size_t(ch) * isz;
+      const bool stage_in = !no_staging && pageable(in), stage_out = !no_staging && pageable(out);
+      if (stage_in && (e = ws->pin_ring_in[0].reserve(in_bytes))) return e;
+      if (stage_out && (e = ws->pin_ring_out[0].reserve(out_bytes))) return e;
+      const unsigned P = unsigned(std::min<size_t>(8, std::max<size_t>(2, in_bytes / (size_t(512) << 10))));
+      if ((e = ws->need_events(2 * size_t(P) + 1))) return e;
+      cudaEvent_t ev_start = ws->events[2 * P];
+      B2_CUDA(cudaMemsetAsync(ws->out_stage.p, 0, out_bytes, st));
+      B2_CUDA(cudaEventRecord(ev_start, st));          // order after earlier work queued on st
+      B2_CUDA(cudaStreamWaitEvent(ws->h2d_stream, ev_start, 0));
+      B2_CUDA(cudaStreamWaitEvent(ws->d2h_stream, ev_start, 0));
+      auto sync_all = [&] { cudaStreamSynchronize(ws->h2d_stream); cudaStreamSynchronize(st); cudaStreamSynchronize(ws->d2h_stream); };
+      CallEmu emu(dp->plan);
+      struct Piece { size_t off, bytes; bool copied; };
+      std::vector<Piece> pieces(P, Piece{0, 0, true});
+      auto drain = [&](unsigned k, bool wait) -> bool {   // piece k's frames: pinned slot -> caller memory
+        if (pieces[k].copied) return true;
+        if (wait) cudaEventSynchronize(ws->events[2 * k + 1]);
+        else if (cudaEventQuery(ws->events[2 * k + 1]) != cudaSuccess) { cudaGetLastError(); return false; }
+        hcopy(static_cast<char *>(out) + pieces[k].off, static_cast<char *>(ws->pin_ring_out[0].p) + pieces[k].off,
+                        pieces[k].bytes);
+        pieces[k].copied = true;
+        return true;
+      };
+      size_t in_done = 0, o_done = 0;
+      unsigned next_drain = 0;
+      for (unsigned k = 0; k < P; ++k) {
+        const bool last = k + 1 == P;
+        const size_t hi = last ? d->ilen : d->ilen * (k + 1) / P;
+        const size_t ioff = in_done * fsz, ilen_b = (hi - in_done) * fsz;
+        const char *src = static_cast<const char *>(in) + ioff;
+        if (stage_in) {
+          hcopy(static_cast<char *>(ws->pin_ring_in[0].p) + ioff, src, ilen_b);
+          src = static_cast<const char *>(ws->pin_ring_in[0].p) + ioff;
+        }
+        if (ilen_b) B2_CUDA(cudaMemcpyAsync(static_cast<char *>(ws->in_stage.p) + ioff, src, ilen_b, cudaMemcpyHostToDevice, ws->h2d_stream));
+        B2_CUDA(cudaEventRecord(ws->events[2 * k], ws->h2d_stream));
+        size_t od = emu.process(hi - in_done, total - o_done);
+        if (last) {
+          od += emu.flush(total - o_done - od);
+          if (o_done + od != total) { sync_all(); return "internal: emulated call partition does not cover the output"; }
+        }
+        in_done = hi;
+        if (od) {
+          B2_CUDA(cudaStreamWaitEvent(st, ws->events[2 * k], 0));
+          SigDesc xin, odsc;
+          xin.p = ws->in_stage.p; xin.dtype = d->dtype; xin.channels = ch;
+          xin.clip_stride = d->in_clip_stride; xin.frame_stride = ch; xin.chan_stride = 1;
+          xin.base = 0; xin.vlo = 0; xin.vhi = long(hi);
+          odsc.p = ws->out_stage.p; odsc.dtype = d->dtype; odsc.channels = ch;
+          odsc.clip_stride = d->out_clip_stride; odsc.frame_stride = ch; odsc.chan_stride = 1; odsc.base = 0;
+          if ((e = run_range(*dp, xin, last ? long(d->ilen) : -1L, ch, ch, long(o_done), long(o_done + od), odsc, ws, st, 0u))) {
+            sync_all();
+            return e;
+          }
+          B2_CUDA(cudaEventRecord(ws->events[2 * k + 1], st));
+          B2_CUDA(cudaStreamWaitEvent(ws->d2h_stream, ws->events[2 * k + 1], 0));
+          const size_t ooff = o_done * fsz, ob = od * fsz;
+          char *dst = stage_out ? static_cast<char *>(ws->pin_ring_out[0].p) + ooff : static_cast<char *>(out) + ooff;
+          B2_CUDA(cudaMemcpyAsync(dst, static_cast<char *>(ws->out_stage.p) + ooff, ob, cudaMemcpyDeviceToHost, ws->d2h_stream));
+          B2_CUDA(cudaEventRecord(ws->events[2 * k + 1], ws->d2h_stream));   // re-recorded: now marks the end of the D2H
+          if (stage_out) pieces[k] = Piece{ooff, ob, false};
+          o_done += od;
+        }
+        // results that have landed meanwhile leave for the caller's array (in order, without waiting)
+        while (stage_out && next_drain < k && drain(next_drain, false)) ++next_drain;
+      }
+      for (; stage_out && next_drain < P; ++next_drain) drain(next_drain, true);
+      sync_all();
+    } else if (n_chunks <= 1 && !no_staging && (in_span + out_span) * isz >= kStageOneMin && (pageable(in) || pageable(out))) {
+      // the one chunk cut into a few pieces: the pool copies piece k + 1 into the pinned slot while piece k is on
+      // the link; on the way back piece k is copied out while piece k + 1 is on the link
+      const size_t ib = in_span * isz, ob = out_span * isz;
+      constexpr size_t kPiece = size_t(768) << 10;
+      const bool stage_in = ib && pageable(in), stage_out = ob && pageable(out);
+      if (stage_in && (e = ws->pin_ring_in[0].reserve(ib))) return e;
+      if (stage_out && (e = ws->pin_ring_out[0].reserve(ob))) return e;
+      const unsigned n_ip = stage_in ? unsigned(std::min<size_t>(4, std::max<size_t>(1, ib / kPiece))) : 1u;
+      for (unsigned k = 0; k < n_ip && ib; ++k) {
+        const size_t lo = (ib * k / n_ip) & ~size_t(255), hi = k + 1 == n_ip ? ib : (ib * (k + 1) / n_ip) & ~size_t(255);
+        const char *src = static_cast<const char *>(in) + lo;
+        if (stage_in) {
+          hcopy(static_cast<char *>(ws->pin_ring_in[0].p) + lo, src, hi - lo);
+          src = static_cast<const char *>(ws->pin_ring_in[0].p) + lo;
+        }
+        B2_CUDA(cudaMemcpyAsync(static_cast<char *>(ws->in_stage.p) + lo, src, hi - lo, cudaMemcpyHostToDevice, st));
+      }
+      if (ob) B2_CUDA(cudaMemsetAsync(ws->out_stage.p, 0, ob, st));
+      if (total && (e = compute(0, d->n_clips, ws->in_stage.p, ws->out_stage.p))) { cudaStreamSynchronize(st); return e; }
+      const unsigned n_op = stage_out ? unsigned(std::min<size_t>(4, std::max<size_t>(1, ob / kPiece))) : 1u;
+      if ((e = ws->need_events(n_op))) { cudaStreamSynchronize(st); return e; }
+      for (unsigned k = 0; k < n_op && ob; ++k) {
+        const size_t lo = (ob * k / n_op) & ~size_t(255), hi = k + 1 == n_op ? ob : (ob * (k + 1) / n_op) & ~size_t(255);
+        char *dst = stage_out ? static_cast<char *>(ws->pin_ring_out[0].p) + lo : static_cast<char *>(out) + lo;
+        B2_CUDA(cudaMemcpyAsync(dst, static_cast<char *>(ws->out_stage.p) + lo, hi - lo, cudaMemcpyDeviceToHost, st));
+        B2_CUDA(cudaEventRecord(ws->events[k], st));
+      }
+      for (unsigned k = 0; k < n_op && ob && stage_out; ++k) {
+        const size_t lo = (ob * k / n_op) & ~size_t(255), hi = k + 1 == n_op ? ob : (ob * (k + 1) / n_op) & ~size_t(255);
+        B2_CUDA(cudaEventSynchronize(ws->events[k]));
+        hcopy(static_cast<char *>(out) + lo, static_cast<char *>(ws->pin_ring_out[0].p) + lo, hi - lo);
+      }
+    } else if (n_chunks <= 1) {
       if (in_span) B2_CUDA(cudaMemcpyAsync(ws->in_stage.p, in, in_span * isz, cudaMemcpyHostToDevice, st));
       if (out_span) B2_CUDA(cudaMemsetAsync(ws->out_stage.p, 0, out_span * isz, st));
       if (total && (e = compute(0, d->n_clips, ws->in_stage.p, ws->out_stage.p))) return e;
@@ -973,15 +1114,7 @@ b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *d, void co
       B2_CUDA(cudaEventRecord(ev_start, st));          // order after earlier work queued on st
       B2_CUDA(cudaStreamWaitEvent(ws->h2d_stream, ev_start, 0));
       B2_CUDA(cudaStreamWaitEvent(ws->d2h_stream, ev_start, 0));
-      // Pageable caller memory (an ordinary ndarray: the drop-in case) cannot be DMA'd directly; the driver's own
-      // staging runs at a fraction of the link.  Such chunks go through three pinned staging slots per direction,
-      // filled / drained by the host copy pool while the copy engines and the kernels work on the other slots.
-      auto pageable = [](const void *ptr) {
-        cudaPointerAttributes pa;
-        if (cudaPointerGetAttributes(&pa, ptr) != cudaSuccess) { cudaGetLastError(); return true; }
-        return pa.type == cudaMemoryTypeUnregistered;
-      };
-      static const bool no_staging = [] { const char *v = std::getenv("B200SOXR_NO_HOST_STAGING"); return v && v[0] == '1'; }();
+      // pageable chunks go through three pinned staging slots per direction
       const bool stage_in = !no_staging && pageable(in), stage_out = !no_staging && pageable(out);
       constexpr unsigned kSlots = 3;
       struct Pending { size_t ooff, obytes; unsigned slot; };

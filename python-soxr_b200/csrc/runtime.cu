@@ -138,7 +138,7 @@ class CopyPool {
     return *pool;
   }
   void run(char *dst, const char *src, size_t bytes) {
-    const size_t kMin = size_t(1) << 20;
+    const size_t kMin = size_t(256) << 10;   // a worker's wake-up costs about as much as copying this
     const unsigned parts = unsigned(std::min<size_t>(workers_.size() + 1, std::max<size_t>(1, bytes / kMin)));
     if (parts <= 1) { std::memcpy(dst, src, bytes); return; }
     const size_t per = ((bytes / parts) + 4095) & ~size_t(4095);

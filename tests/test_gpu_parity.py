@@ -187,6 +187,32 @@ def test_length_match(length):
         assert np.all(y_oneshot == y_split)
 
 
+@pytest.mark.parametrize('in_rate, out_rate, quality, dtype, channels, frames', [
+    (48000, 44100, 'HQ', np.float32, 2, 400001),
+    (48000, 44100, 'HQ', np.float32, 1, 480000),      # BASELINE configs[0]
+    (44100, 48000, 'VHQ', np.float64, 2, 300017),
+    (47999, 44100, 'HQ', np.float32, 1, 600000),      # irrational: interpolated-coefficient stage behind the DFT stage
+    (96000, 16000, 'MQ', np.float32, 3, 350003),
+    (44100, 48000, 'QQ', np.float32, 2, 500000),
+    (8000, 48000, 'HQ', np.float32, 2, 200000),
+])
+def test_time_split_single_clip(in_rate, out_rate, quality, dtype, channels, frames):
+    # one large C-ordered ndarray through soxr.resample runs cut in time (piece k + 1 copied in while piece k is
+    # computed and copied back, api.cu); the Fortran-ordered twin of the same data takes the unsplit path and a
+    # ResampleStream fed odd chunks is the third evaluation of the same block grid: all bit for bit equal
+    x = np.random.default_rng(frames).standard_normal((frames, channels)).astype(dtype)
+    y = soxr.resample(x if channels > 1 else x[:, 0], in_rate, out_rate, quality)
+    y = y.reshape(len(y), channels)
+    assert y.shape[0] == int(frames * out_rate / in_rate + .5)
+    if channels > 1:
+        y_unsplit = soxr.resample(np.asfortranarray(x), in_rate, out_rate, quality)
+        assert np.array_equal(y, y_unsplit)
+    y_stream, _, _ = _stream(x, in_rate, out_rate, 70001, dtype, quality)
+    assert np.array_equal(y, y_stream)
+    y_one = soxr._resample_oneshot(x, in_rate, out_rate, quality)
+    assert np.array_equal(y, y_one.reshape(y.shape))
+
+
 @pytest.mark.parametrize('channels', [1, 2, 3, 5, 7, 24, 49])
 def test_channel_match(channels):
     # reference tests/test_resample.py:74-84
