@@ -971,13 +971,17 @@ b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *d, void co
       return pa.type == cudaMemoryTypeUnregistered;
     };
     static const bool no_staging = [] { const char *v = std::getenv("B200SOXR_NO_HOST_STAGING"); return v && v[0] == '1'; }();
-    // Staging copies of a small call stay on the calling thread: waking the pool's workers costs 50-100 us of jitter
-    // on a virtualised host, more than they save below a few MB (profiles/r4f_time_split.log).
-    static const size_t kPoolMin = [] {
-      const char *v = std::getenv("B200SOXR_POOL_MIN_KB");
-      return size_t(v ? std::max(0L, std::atol(v)) : 8192) << 10;
-    }();
-    const bool pool_copies = (in_span + out_span) * isz >= kPoolMin;
+    // Who copies between the caller's pageable memory and the pinned slots of a single-chunk call.  Measured on a
+    // 16-vCPU host (profiles/r4h_pool_small.log, r4i, r4j; p50 over 100 calls): from about 2 MB in + out the pool
+    // wins for multi-channel clips (5 s stereo float32 0.28 -> 0.21 ms, 10 s stereo int16 0.39 -> 0.27, 2.5 s stereo VHQ
+    // 0.21 -> 0.14 when it is allowed at 1.8 MB), but a mono clip of the same size is bound by its transforms (twice
+    // the blocks per byte), hides the calling thread's copies behind them and only inherits the pool's run-to-run
+    // spread (10 s mono: 0.38 ms on the calling thread, 0.37 - 0.54 with the pool; spinning workers or a polling
+    // caller did not change that).  B200SOXR_POOL_MIN_KB overrides the size rule.
+    static const long kPoolMinKb = [] { const char *v = std::getenv("B200SOXR_POOL_MIN_KB"); return v ? std::atol(v) : -1L; }();
+    const size_t io_bytes = (in_span + out_span) * isz;
+    const bool pool_copies = kPoolMinKb >= 0 ? io_bytes >= (size_t(kPoolMinKb) << 10)
+                                             : io_bytes >= (size_t(8) << 20) || (d->channels >= 2 && io_bytes >= (size_t(1536) << 10));
     auto hcopy = [&](void *dst, const void *src, size_t n) {
       if (pool_copies) parallel_memcpy(dst, src, n); else std::memcpy(dst, src, n);
     };
