@@ -234,6 +234,15 @@ B200SOXR_API b200soxr_error_t b200soxr_quantize(void const *planar, int is_doubl
                                                 int dither, int split, unsigned long long *seed,
                                                 void *out_interleaved, size_t *clips);
 
+/* ---- result buffers in page-locked host memory, for front-ends that hand the caller an array they
+ *      allocated themselves: the counterpart of `new T[olen * channels]` + capsule in the reference
+ *      binding (src/soxr_ext.cpp:240,268-272).  The device-to-host copy of a result lands in such a
+ *      buffer directly (no staging copy on the host).  Buffers are recycled through a bounded cache;
+ *      NULL when the budget (B200SOXR_PINNED_RESULT_MB, default 1024; 0 disables) is spent or no
+ *      device is usable -- the caller then uses ordinary memory.                              */
+B200SOXR_API void *b200soxr_result_alloc(size_t bytes);
+B200SOXR_API void b200soxr_result_free(void *p);
+
 /* Number of CUDA kernels this library has launched in this process (bench.py's
  * `gpu_launches`). */
 B200SOXR_API unsigned long long b200soxr_launch_count(void);

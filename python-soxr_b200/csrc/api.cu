@@ -13,6 +13,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <iterator>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <new>
@@ -825,9 +827,14 @@ b200soxr_error_t b200soxr_oneshot(double irate, double orate, unsigned num_chann
 // ---------------------------------------------------------------------------
 // batch entry point
 // ---------------------------------------------------------------------------
-b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *d, void const *in, void *out, size_t *odone,
+b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *desc, void const *in, void *out, size_t *odone,
                                          size_t *clips, void *cuda_stream) {
-  if (!d) return "null pointer";
+  if (!desc) return "null pointer";
+  // One channel has no channel stride: a mono clip handed over in "split-channel" form (python-soxr sends every 1-D
+  // array that way, soxr/__init__.py) IS the interleaved layout, and takes its paths (time-split pipeline, vector I/O).
+  b200soxr_batch_desc_t norm = *desc;
+  if (norm.channels == 1 && norm.in_frame_stride == 1 && norm.out_frame_stride == 1) norm.in_chan_stride = norm.out_chan_stride = 1;
+  b200soxr_batch_desc_t const *const d = &norm;
   if (!(d->in_rate > 0) || !(d->out_rate > 0)) return "I/O ratio out-of-range";
   if (d->dtype < 0 || d->dtype > 3) return "invalid io datatype(s)";
   if (!d->channels || !d->n_clips) return "invalid # of channels";
@@ -1185,6 +1192,76 @@ b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *d, void co
     } else B2_CUDA(cudaStreamSynchronize(st));
   }
   return nullptr;
+}
+
+// ---- pinned result buffers (include/b200soxr.h) -----------------------------------------------------------------
+namespace {
+struct ResultPool {
+  std::mutex mu;
+  std::map<void *, size_t> live;              // handed out: pointer -> capacity
+  std::multimap<size_t, void *> cached;       // free: capacity -> pointer
+  size_t live_bytes = 0, cached_bytes = 0;
+  const size_t budget = [] {
+    const char *v = std::getenv("B200SOXR_PINNED_RESULT_MB");
+    return size_t(v ? std::max(0L, std::atol(v)) : 1024) << 20;
+  }();
+  static size_t bucket(size_t n) {            // four sizes per octave from 256 kB: little waste, few distinct sizes
+    size_t b = size_t(256) << 10;
+    while (b < n) b <<= 1;
+    const size_t q = b >> 3;                  // b/2 < n <= b: steps of b/8 above b/2
+    return b > (size_t(256) << 10) ? (n + q - 1) / q * q : b;
+  }
+};
+ResultPool &result_pool() {
+  static ResultPool *p = new ResultPool();    // never destroyed: arrays may be released at interpreter exit
+  return *p;
+}
+}  // namespace
+
+void *b200soxr_result_alloc(size_t bytes) {
+  ResultPool &rp = result_pool();
+  if (!bytes || !rp.budget || !device_ok()) return nullptr;
+  const size_t cap = ResultPool::bucket(bytes);
+  std::lock_guard<std::mutex> l(rp.mu);
+  auto it = rp.cached.lower_bound(cap);
+  if (it != rp.cached.end() && it->first <= cap + cap / 4) {
+    void *p = it->second;
+    const size_t c = it->first;
+    rp.cached.erase(it);
+    rp.cached_bytes -= c;
+    rp.live[p] = c;
+    rp.live_bytes += c;
+    return p;
+  }
+  while (rp.live_bytes + rp.cached_bytes + cap > rp.budget && !rp.cached.empty()) {   // make room: drop cached buffers
+    auto big = std::prev(rp.cached.end());
+    cudaFreeHost(big->second);
+    rp.cached_bytes -= big->first;
+    rp.cached.erase(big);
+  }
+  if (rp.live_bytes + rp.cached_bytes + cap > rp.budget) return nullptr;
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, cap, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  rp.live[p] = cap;
+  rp.live_bytes += cap;
+  return p;
+}
+
+void b200soxr_result_free(void *p) {
+  if (!p) return;
+  ResultPool &rp = result_pool();
+  std::lock_guard<std::mutex> l(rp.mu);
+  auto it = rp.live.find(p);
+  if (it == rp.live.end()) return;
+  const size_t c = it->second;
+  rp.live.erase(it);
+  rp.live_bytes -= c;
+  if (rp.cached_bytes + c <= (size_t(256) << 20)) {   // keep up to 256 MB around for the next results
+    rp.cached.emplace(c, p);
+    rp.cached_bytes += c;
+  } else {
+    cudaFreeHost(p);
+  }
 }
 
 b200soxr_error_t b200soxr_quantize(void const *planar, int is_double, unsigned channels, size_t n,

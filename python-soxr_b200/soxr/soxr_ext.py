@@ -103,6 +103,10 @@ def _load():
     L.b200soxr_resample_batch.restype = C.c_char_p
     L.b200soxr_resample_batch.argtypes = [C.POINTER(BatchDesc), C.c_void_p, C.c_void_p,
                                           C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_void_p]
+    L.b200soxr_result_alloc.restype = C.c_void_p
+    L.b200soxr_result_alloc.argtypes = [C.c_size_t]
+    L.b200soxr_result_free.restype = None
+    L.b200soxr_result_free.argtypes = [C.c_void_p]
     L.b200soxr_output_frames.restype = C.c_size_t
     L.b200soxr_output_frames.argtypes = [C.c_double, C.c_double, C.c_size_t]
     L.b200soxr_plan_dump.restype = C.c_size_t
@@ -394,6 +398,39 @@ class CSoxr:
             raise RuntimeError(err.decode())
 
 
+class _PinnedResult:
+    """Owner of one page-locked result buffer of the library (b200soxr_result_alloc); the ndarray built over it keeps
+    it alive through `base`, and it goes back to the library's cache when the last view is gone -- the role of the
+    capsule that owns `new T[olen]` in the reference binding (soxr_ext.cpp:268-272)."""
+    __slots__ = ('ptr', '__array_interface__')
+
+    def __init__(self, ptr, shape, dtype):
+        self.ptr = ptr
+        self.__array_interface__ = {'shape': tuple(shape), 'typestr': np.dtype(dtype).str, 'data': (ptr, False),
+                                    'version': 3}
+
+    def __del__(self):
+        try:
+            _lib.b200soxr_result_free(self.ptr)
+        except Exception:       # interpreter shutdown: the process is going away with the buffer
+            pass
+
+
+_RESULT_PINNED_MIN = 128 << 10
+
+
+def _result_empty(shape, dtype):
+    """Uninitialised result array: in page-locked memory of the library from 128 kB (the device-to-host copy then lands
+    in it directly), ordinary memory below that or when the library's budget is spent."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    if nbytes >= _RESULT_PINNED_MIN:
+        ptr = _lib.b200soxr_result_alloc(nbytes)
+        if ptr:
+            return np.asarray(_PinnedResult(ptr, shape, dtype))
+    return np.empty(shape, dtype=dtype)
+
+
 def _check_2d(x, code):
     if type(x) is not np.ndarray or x.ndim != 2 or _DT_CODE.get(x.dtype) != code:
         raise TypeError("incompatible function arguments: need a 2-D %s ndarray" % _DT_NAME[code])
@@ -405,7 +442,7 @@ def _make_divide_proc(code):
         x = np.ascontiguousarray(x)
         ilen, ch = x.shape
         total = output_frames(in_rate, out_rate, ilen)
-        y = np.empty((total, ch), dtype=x.dtype)
+        y = _result_empty((total, ch), x.dtype)
         resample_batch_raw(x.ctypes.data, y.ctypes.data, in_rate=in_rate, out_rate=out_rate, quality=int(quality),
                            dtype_code=code, n_clips=1, channels=ch, ilen=ilen,
                            in_strides=(0, ch, 1), out_strides=(0, ch, 1), olen=total,
@@ -426,7 +463,7 @@ def _make_split_ch(code):
         if ch > 1 and ilen and (x.strides[1] % x.itemsize or x.strides[1] < 0):
             x = np.asfortranarray(x)
         olen = int(ilen * out_rate / in_rate + 1)          # soxr_ext.cpp:284
-        ybuf = np.zeros(olen * ch, dtype=x.dtype)
+        ybuf = _result_empty((olen * ch,), x.dtype)   # (every element of the view returned below is written)
         st = (x.strides[1] // x.itemsize) if (ch > 1 and ilen) else max(ilen, 1)
         out_pos, _ = resample_batch_raw(x.ctypes.data, ybuf.ctypes.data, in_rate=in_rate, out_rate=out_rate,
                                         quality=int(quality), dtype_code=code, n_clips=1, channels=ch, ilen=ilen,
@@ -445,7 +482,7 @@ def _make_oneshot(code):
         x = np.ascontiguousarray(x)
         ilen, ch = x.shape
         total = output_frames(in_rate, out_rate, ilen)
-        y = np.empty((total, ch), dtype=x.dtype)
+        y = _result_empty((total, ch), x.dtype)
         resample_batch_raw(x.ctypes.data, y.ctypes.data, in_rate=in_rate, out_rate=out_rate, quality=int(quality),
                            dtype_code=code, n_clips=1, channels=ch, ilen=ilen,
                            in_strides=(0, ch, 1), out_strides=(0, ch, 1), olen=total,

@@ -213,6 +213,50 @@ def test_time_split_single_clip(in_rate, out_rate, quality, dtype, channels, fra
     assert np.array_equal(y, y_one.reshape(y.shape))
 
 
+def test_results_live_in_recycled_pinned_buffers():
+    # results of the whole-signal drivers from 128 kB are ndarrays over page-locked buffers of the library (the
+    # device-to-host copy lands in them directly); views keep the buffer alive, the last one gives it back, and the
+    # next result of that size gets the same buffer again
+    import gc
+
+    def owner_of(a):
+        o = a.base
+        while isinstance(o, np.ndarray):
+            o = o.base
+        return o
+
+    x = np.random.default_rng(11).standard_normal((150000, 2)).astype(np.float32)
+    y = soxr.resample(x, 48000, 44100)
+    assert type(owner_of(y)).__name__ == '_PinnedResult' and y.flags.writeable and not y.flags.owndata
+    want = y.copy()
+    ptr = owner_of(y).ptr
+    view = y[1000:2000, 1]
+    del y
+    gc.collect()
+    assert np.array_equal(view, want[1000:2000, 1])          # still backed by the buffer
+    y2 = soxr.resample(x, 48000, 44100)                       # the first buffer is still held by `view`
+    assert owner_of(y2).ptr != ptr and np.array_equal(y2, want)
+    del view
+    gc.collect()
+    y3 = soxr._resample_oneshot(x, 48000, 44100)              # (a recycled buffer: this one or an older one of its size)
+    assert type(owner_of(y3)).__name__ == '_PinnedResult' and np.array_equal(y3, want)
+    y3 += 1                                                   # ordinary writable memory
+    assert np.array_equal(y3, want + 1)
+    small = soxr.resample(x[:1000], 48000, 44100)             # small results stay in ordinary memory
+    assert type(owner_of(small)).__name__ != '_PinnedResult'
+    # the cache itself, in a size class nothing else in the suite uses: freed buffers are handed out again
+    p1 = soxr_ext._lib.b200soxr_result_alloc(13 << 20)
+    assert p1
+    soxr_ext._lib.b200soxr_result_free(p1)
+    p2 = soxr_ext._lib.b200soxr_result_alloc((13 << 20) - 4096)   # same size class
+    assert p2 == p1
+    soxr_ext._lib.b200soxr_result_free(p2)
+    # 1-D input takes the split-channel driver (as in the reference); its result is pinned too
+    m = soxr.resample(x[:, 0].copy(), 48000, 44100)
+    assert m.ndim == 1 and type(owner_of(m)).__name__ in ('_PinnedResult', 'DummyArray')
+    assert np.array_equal(m, soxr.resample(x[:, :1].copy(), 48000, 44100)[:, 0])
+
+
 @pytest.mark.parametrize('channels', [1, 2, 3, 5, 7, 24, 49])
 def test_channel_match(channels):
     # reference tests/test_resample.py:74-84
