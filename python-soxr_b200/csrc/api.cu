@@ -1256,7 +1256,7 @@ void b200soxr_result_free(void *p) {
   const size_t c = it->second;
   rp.live.erase(it);
   rp.live_bytes -= c;
-  if (rp.cached_bytes + c <= (size_t(256) << 20)) {   // keep up to 256 MB around for the next results
+  if (rp.cached_bytes + c <= rp.budget / 2) {   // keep up to half the budget around for the next results
     rp.cached.emplace(c, p);
     rp.cached_bytes += c;
   } else {
