@@ -1009,14 +1009,17 @@ b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *desc, void
     const bool time_split = d->n_clips == 1 && (d->flags & B200SOXR_BATCH_EXACT_GRID) && !int_out && total &&
                             d->in_chan_stride == 1 && d->in_frame_stride == (long long)d->channels &&
                             d->out_chan_stride == 1 && d->out_frame_stride == (long long)d->channels &&
-                            in_bytes >= kTimeSplitMin && in_bytes + out_bytes <= (size_t(1) << 30);
+                            in_bytes >= kTimeSplitMin;
+    // Pieces of a single-chunk call go through rings of three pinned slots per direction (a slot is reused once its
+    // previous tenant has left), so the page-locked staging memory is bounded by the piece size, not by the call.
+    constexpr unsigned kRing = 3;
+    constexpr size_t kPieceMax = size_t(8) << 20;
     if (time_split) {
       const unsigned ch = d->channels;
       const size_t fsz = size_t(ch) * isz;
       const bool stage_in = !no_staging && pageable(in), stage_out = !no_staging && pageable(out);
-      if (stage_in && (e = ws->pin_ring_in[0].reserve(in_bytes))) return e;
-      if (stage_out && (e = ws->pin_ring_out[0].reserve(out_bytes))) return e;
-      const unsigned P = unsigned(std::min<size_t>(8, std::max<size_t>(2, in_bytes / (size_t(512) << 10))));
+      const size_t piece_b = std::min(kPieceMax, std::max<size_t>(size_t(512) << 10, in_bytes / 8));
+      const unsigned P = unsigned(std::max<size_t>(2, in_bytes / piece_b));   // (a piece stays below 2 * kPieceMax)
       if ((e = ws->need_events(2 * size_t(P) + 1))) return e;
       cudaEvent_t ev_start = ws->events[2 * P];
       B2_CUDA(cudaMemsetAsync(ws->out_stage.p, 0, out_bytes, st));
@@ -1031,8 +1034,7 @@ b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *desc, void
         if (pieces[k].copied) return true;
         if (wait) cudaEventSynchronize(ws->events[2 * k + 1]);
         else if (cudaEventQuery(ws->events[2 * k + 1]) != cudaSuccess) { cudaGetLastError(); return false; }
-        hcopy(static_cast<char *>(out) + pieces[k].off, static_cast<char *>(ws->pin_ring_out[0].p) + pieces[k].off,
-                        pieces[k].bytes);
+        hcopy(static_cast<char *>(out) + pieces[k].off, ws->pin_ring_out[k % kRing].p, pieces[k].bytes);
         pieces[k].copied = true;
         return true;
       };
@@ -1043,9 +1045,12 @@ b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *desc, void
         const size_t hi = last ? d->ilen : d->ilen * (k + 1) / P;
         const size_t ioff = in_done * fsz, ilen_b = (hi - in_done) * fsz;
         const char *src = static_cast<const char *>(in) + ioff;
-        if (stage_in) {
-          hcopy(static_cast<char *>(ws->pin_ring_in[0].p) + ioff, src, ilen_b);
-          src = static_cast<const char *>(ws->pin_ring_in[0].p) + ioff;
+        if (stage_in && ilen_b) {
+          PinnedBuf &slot = ws->pin_ring_in[k % kRing];
+          if (k >= kRing) B2_CUDA(cudaEventSynchronize(ws->events[2 * (k - kRing)]));   // its previous tenant is on the device
+          if ((e = slot.reserve(ilen_b))) { sync_all(); return e; }
+          hcopy(slot.p, src, ilen_b);
+          src = static_cast<const char *>(slot.p);
         }
         if (ilen_b) B2_CUDA(cudaMemcpyAsync(static_cast<char *>(ws->in_stage.p) + ioff, src, ilen_b, cudaMemcpyHostToDevice, ws->h2d_stream));
         B2_CUDA(cudaEventRecord(ws->events[2 * k], ws->h2d_stream));
@@ -1070,7 +1075,13 @@ b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *desc, void
           B2_CUDA(cudaEventRecord(ws->events[2 * k + 1], st));
           B2_CUDA(cudaStreamWaitEvent(ws->d2h_stream, ws->events[2 * k + 1], 0));
           const size_t ooff = o_done * fsz, ob = od * fsz;
-          char *dst = stage_out ? static_cast<char *>(ws->pin_ring_out[0].p) + ooff : static_cast<char *>(out) + ooff;
+          char *dst = static_cast<char *>(out) + ooff;
+          if (stage_out) {
+            while (next_drain + kRing <= k) drain(next_drain++, true);   // the slot's previous tenant has been copied out
+            PinnedBuf &slot = ws->pin_ring_out[k % kRing];
+            if ((e = slot.reserve(ob))) { sync_all(); return e; }
+            dst = static_cast<char *>(slot.p);
+          }
           B2_CUDA(cudaMemcpyAsync(dst, static_cast<char *>(ws->out_stage.p) + ooff, ob, cudaMemcpyDeviceToHost, ws->d2h_stream));
           B2_CUDA(cudaEventRecord(ws->events[2 * k + 1], ws->d2h_stream));   // re-recorded: now marks the end of the D2H
           if (stage_out) pieces[k] = Piece{ooff, ob, false};
@@ -1082,38 +1093,51 @@ b200soxr_error_t b200soxr_resample_batch(b200soxr_batch_desc_t const *desc, void
       for (; stage_out && next_drain < P; ++next_drain) drain(next_drain, true);
       sync_all();
     } else if (n_chunks <= 1 && !no_staging && (in_span + out_span) * isz >= kStageOneMin && (pageable(in) || pageable(out))) {
-      // the one chunk cut into a few pieces: the pool copies piece k + 1 into the pinned slot while piece k is on
-      // the link; on the way back piece k is copied out while piece k + 1 is on the link
+      // the one chunk cut into pieces: piece k + 1 is copied into its pinned slot while piece k is on the link; on
+      // the way back piece k is copied out while piece k + 1 is on the link
       const size_t ib = in_span * isz, ob = out_span * isz;
       constexpr size_t kPiece = size_t(768) << 10;
       const bool stage_in = ib && pageable(in), stage_out = ob && pageable(out);
-      if (stage_in && (e = ws->pin_ring_in[0].reserve(ib))) return e;
-      if (stage_out && (e = ws->pin_ring_out[0].reserve(ob))) return e;
-      const unsigned n_ip = stage_in ? unsigned(std::min<size_t>(4, std::max<size_t>(1, ib / kPiece))) : 1u;
+      auto n_pieces = [&](size_t bytes) {
+        return unsigned(std::max<size_t>(std::min<size_t>(4, std::max<size_t>(1, bytes / kPiece)), (bytes + kPieceMax - 1) / kPieceMax));
+      };
+      auto cut = [](size_t bytes, unsigned k, unsigned n) { return k >= n ? bytes : (bytes * k / n) & ~size_t(255); };
+      const unsigned n_ip = stage_in ? n_pieces(ib) : 1u, n_op = stage_out ? n_pieces(ob) : 1u;
+      if ((e = ws->need_events(size_t(n_ip) + n_op))) return e;
       for (unsigned k = 0; k < n_ip && ib; ++k) {
-        const size_t lo = (ib * k / n_ip) & ~size_t(255), hi = k + 1 == n_ip ? ib : (ib * (k + 1) / n_ip) & ~size_t(255);
+        const size_t lo = cut(ib, k, n_ip), hi = cut(ib, k + 1, n_ip);
         const char *src = static_cast<const char *>(in) + lo;
         if (stage_in) {
-          hcopy(static_cast<char *>(ws->pin_ring_in[0].p) + lo, src, hi - lo);
-          src = static_cast<const char *>(ws->pin_ring_in[0].p) + lo;
+          PinnedBuf &slot = ws->pin_ring_in[k % kRing];
+          if (k >= kRing) B2_CUDA(cudaEventSynchronize(ws->events[k - kRing]));
+          if ((e = slot.reserve(hi - lo))) { cudaStreamSynchronize(st); return e; }
+          hcopy(slot.p, src, hi - lo);
+          src = static_cast<const char *>(slot.p);
         }
         B2_CUDA(cudaMemcpyAsync(static_cast<char *>(ws->in_stage.p) + lo, src, hi - lo, cudaMemcpyHostToDevice, st));
+        B2_CUDA(cudaEventRecord(ws->events[k], st));
       }
       if (ob) B2_CUDA(cudaMemsetAsync(ws->out_stage.p, 0, ob, st));
       if (total && (e = compute(0, d->n_clips, ws->in_stage.p, ws->out_stage.p))) { cudaStreamSynchronize(st); return e; }
-      const unsigned n_op = stage_out ? unsigned(std::min<size_t>(4, std::max<size_t>(1, ob / kPiece))) : 1u;
-      if ((e = ws->need_events(n_op))) { cudaStreamSynchronize(st); return e; }
+      unsigned drained = 0;
+      auto drain_out = [&](unsigned k) {
+        const size_t lo = cut(ob, k, n_op), hi = cut(ob, k + 1, n_op);
+        cudaEventSynchronize(ws->events[n_ip + k]);
+        hcopy(static_cast<char *>(out) + lo, ws->pin_ring_out[k % kRing].p, hi - lo);
+      };
       for (unsigned k = 0; k < n_op && ob; ++k) {
-        const size_t lo = (ob * k / n_op) & ~size_t(255), hi = k + 1 == n_op ? ob : (ob * (k + 1) / n_op) & ~size_t(255);
-        char *dst = stage_out ? static_cast<char *>(ws->pin_ring_out[0].p) + lo : static_cast<char *>(out) + lo;
+        const size_t lo = cut(ob, k, n_op), hi = cut(ob, k + 1, n_op);
+        char *dst = static_cast<char *>(out) + lo;
+        if (stage_out) {
+          while (drained + kRing <= k) drain_out(drained++);
+          PinnedBuf &slot = ws->pin_ring_out[k % kRing];
+          if ((e = slot.reserve(hi - lo))) { cudaStreamSynchronize(st); return e; }
+          dst = static_cast<char *>(slot.p);
+        }
         B2_CUDA(cudaMemcpyAsync(dst, static_cast<char *>(ws->out_stage.p) + lo, hi - lo, cudaMemcpyDeviceToHost, st));
-        B2_CUDA(cudaEventRecord(ws->events[k], st));
+        B2_CUDA(cudaEventRecord(ws->events[n_ip + k], st));
       }
-      for (unsigned k = 0; k < n_op && ob && stage_out; ++k) {
-        const size_t lo = (ob * k / n_op) & ~size_t(255), hi = k + 1 == n_op ? ob : (ob * (k + 1) / n_op) & ~size_t(255);
-        B2_CUDA(cudaEventSynchronize(ws->events[k]));
-        hcopy(static_cast<char *>(out) + lo, static_cast<char *>(ws->pin_ring_out[0].p) + lo, hi - lo);
-      }
+      for (; stage_out && ob && drained < n_op; ++drained) drain_out(drained);
     } else if (n_chunks <= 1) {
       if (in_span) B2_CUDA(cudaMemcpyAsync(ws->in_stage.p, in, in_span * isz, cudaMemcpyHostToDevice, st));
       if (out_span) B2_CUDA(cudaMemsetAsync(ws->out_stage.p, 0, out_span * isz, st));
