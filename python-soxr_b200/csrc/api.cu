@@ -1280,6 +1280,14 @@ void b200soxr_result_free(void *p) {
   const size_t c = it->second;
   rp.live.erase(it);
   rp.live_bytes -= c;
+  constexpr size_t kBig = size_t(64) << 20;
+  if (c >= kBig) {   // at most one large buffer stays cached (enough for `y = f(x)` in a loop: one live, one free)
+    for (auto jt = rp.cached.lower_bound(kBig); jt != rp.cached.end();) {
+      cudaFreeHost(jt->second);
+      rp.cached_bytes -= jt->first;
+      jt = rp.cached.erase(jt);
+    }
+  }
   if (rp.cached_bytes + c <= rp.budget / 2) {   // keep up to half the budget around for the next results
     rp.cached.emplace(c, p);
     rp.cached_bytes += c;

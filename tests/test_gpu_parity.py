@@ -261,6 +261,15 @@ def test_results_live_in_recycled_pinned_buffers():
     p2 = soxr_ext._lib.b200soxr_result_alloc((13 << 20) - 4096)   # same size class
     assert p2 == p1
     soxr_ext._lib.b200soxr_result_free(p2)
+    # large buffers (64 MB and up): at most one stays cached
+    L = soxr_ext._lib
+    a, b = L.b200soxr_result_alloc(100 << 20), L.b200soxr_result_alloc(100 << 20)
+    assert a and b and a != b
+    L.b200soxr_result_free(a)
+    L.b200soxr_result_free(b)          # drops `a` from the cache
+    c = L.b200soxr_result_alloc(100 << 20)
+    assert c == b
+    L.b200soxr_result_free(c)
     # 1-D input takes the split-channel driver (as in the reference); its result is pinned too
     m = soxr.resample(x[:, 0].copy(), 48000, 44100)
     assert m.ndim == 1 and type(owner_of(m)).__name__ in ('_PinnedResult', 'DummyArray')
